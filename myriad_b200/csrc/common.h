@@ -1,0 +1,43 @@
+// Host-side helpers shared by all translation units of libmyriad_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/myriad_b200.h"
+
+namespace myr {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+// cuTensorMapEncodeTiled obtained through the runtime (no link-time libcuda dependency).
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1; box in elements. fp16, SWIZZLE_128B.
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box);
+
+#define MYR_CHECK_ARG(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      myr::set_error(__VA_ARGS__);        \
+      return MYR_ERR_INVALID;             \
+    }                                     \
+  } while (0)
+
+#define MYR_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      myr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MYR_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define MYR_CHECK_LAUNCH() MYR_CHECK_CUDA(cudaGetLastError())
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace myr

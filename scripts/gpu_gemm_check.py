@@ -1,0 +1,90 @@
+"""GPU check of myr_gemm_f16 vs torch (fp32 reference of the same fp16 operands) + timing. Run under gpurun."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from myriad_b200 import kernels as K
+
+torch.manual_seed(0)
+dev = torch.device("cuda:0")
+
+def ref(x, w, bias=None, act=0, res=None):
+    y = x.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias.float()
+    if act == 1:
+        y = torch.nn.functional.gelu(y.half().float()).half().float() if False else torch.nn.functional.gelu(y)
+    if res is not None:
+        y = y + res.float()
+    return y
+
+def run(T, F, Kd, bias=False, act=0, res=None, out_dtype=torch.float16, **kw):
+    x = torch.randn(T, Kd, device=dev).half()
+    w = (torch.randn(F, Kd, device=dev) / Kd ** 0.5).half()
+    b = torch.randn(F, device=dev).half() if bias else None
+    r = None
+    if res == "f16":
+        r = torch.randn(T, F, device=dev).half()
+    elif res == "f32":
+        r = torch.randn(T, F, device=dev)
+    y = K.gemm(x, w, bias=b, act=act, res=r, out_dtype=out_dtype, **kw)
+    torch.cuda.synchronize()
+    yr = ref(x, w, b, act, r)
+    err = (y.float() - yr).abs().max().item()
+    tol = 2e-2 if out_dtype == torch.float16 else 2e-3
+    ok = err < tol and torch.isfinite(y.float()).all().item()
+    print("T=%5d F=%5d K=%5d bias=%d act=%d res=%s out=%s kw=%s  max_err=%.3e %s" % (
+        T, F, Kd, bias, act, res, str(out_dtype)[6:], kw, err, "OK" if ok else "FAIL"), flush=True)
+    return ok
+
+def bench(T, F, Kd, iters=20, **kw):
+    x = torch.randn(T, Kd, device=dev).half()
+    w = (torch.randn(F, Kd, device=dev) / Kd ** 0.5).half()
+    out = torch.empty(T, F, device=dev, dtype=torch.float16)
+    for _ in range(3):
+        K.gemm(x, w, out=out, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        K.gemm(x, w, out=out, **kw)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    for _ in range(3):
+        torch.matmul(x, w.t(), out=out)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(x, w.t(), out=out)
+    e1.record(); torch.cuda.synchronize()
+    ms_t = e0.elapsed_time(e1) / iters
+    fl = 2.0 * T * F * Kd
+    by = 2.0 * (T * Kd + F * Kd + T * F)
+    print("bench T=%5d F=%5d K=%5d %s: ours %.3f ms %.1f TF/s %.0f GB/s | cublas %.3f ms %.1f TF/s" % (
+        T, F, Kd, kw, ms, fl / ms / 1e9, by / ms / 1e6, ms_t, fl / ms_t / 1e9), flush=True)
+
+ok = True
+print("sm count", K.lib().myr_device_sm_count())
+# basic shapes first (single tile, single k-block)
+ok &= run(16, 128, 64)
+ok &= run(16, 128, 128)
+ok &= run(256, 128, 64)
+ok &= run(256, 256, 512)
+ok &= run(100, 200, 136)
+ok &= run(2056, 4224, 1408, bias=True)
+ok &= run(2056, 1408, 1408, bias=True, res="f32", out_dtype=torch.float32)
+ok &= run(2056, 6144, 1408, bias=True, act=1)
+ok &= run(2056, 1408, 6144, bias=True, res="f16")
+ok &= run(4, 4096, 4096)
+ok &= run(4, 11008, 4096)
+ok &= run(4, 4096, 11008, res="f32", out_dtype=torch.float32)
+ok &= run(4, 32000, 4096, out_dtype=torch.float32)
+ok &= run(524, 12288, 4096)
+ok &= run(257, 768, 1408, bias=True)
+ok &= run(81, 3072, 768, bias=True, act=1)
+ok &= run(300, 256, 512, bn_hint=64)
+ok &= run(300, 256, 4096, ksplit_hint=4)
+print("ALL OK" if ok else "SOME FAILED", flush=True)
+for shp in [(2056, 4224, 1408), (2056, 6144, 1408), (2056, 1408, 6144), (2056, 1408, 1408), (8224, 6144, 1408),
+            (4, 4096, 4096), (4, 22016, 4096), (4, 4096, 11008), (4, 32000, 4096), (524, 12288, 4096),
+            (524, 22016, 4096), (524, 4096, 11008), (8192, 8192, 8192)]:
+    bench(*shp)
