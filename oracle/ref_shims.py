@@ -170,7 +170,4 @@ def build_llama(hidden, layers, heads, inter, vocab, max_pos=2048, eps=1e-6):
                       max_position_embeddings=max_pos, rms_norm_eps=eps, hidden_act="silu",
                       pad_token_id=0, bos_token_id=1, eos_token_id=2, tie_word_embeddings=False)
     cfg.use_cache = True
-    cfg.output_attentions = False
-    cfg.output_hidden_states = False
-    cfg.use_return_dict = True
     return m.LlamaForCausalLM(cfg).eval()

@@ -1,0 +1,88 @@
+"""CPU: the oracle restatement (oracle/myriad_oracle.py) must reproduce the outputs the UNMODIFIED reference
+modules produced in the build container (tests/golden/*.npz, written by oracle/gen_golden.py)."""
+import numpy as np
+import torch
+
+from myriad_b200 import synthetic as syn
+from oracle import myriad_oracle as O
+
+TOL = 5e-5  # fp32 CPU vs fp32 CPU, different op order only
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _assert_close(a, b, tol=TOL):
+    err = (a - b).abs().max().item()
+    assert err <= tol * max(1.0, b.abs().max().item()), err
+
+
+def test_vit_tiny(golden):
+    g = golden("vit_tiny")
+    d = syn.tiny_dims()
+    sd = syn.make_state_dict(d, int(g["seed"]), only_prefix="visual_encoder")
+    image, _ = syn.make_inputs(2, seed=int(g["input_seed"]), img=d.vit.img)
+    _assert_close(O.vit_patch_embed(sd, image, d.vit), _t(g["patch_embed"]))
+    _assert_close(O.vit_forward(sd, image, d.vit), _t(g["out"]))
+
+
+def test_qformer_tiny(golden):
+    g = golden("qformer_tiny")
+    d = syn.tiny_dims()
+    sd = syn.make_state_dict(d, int(g["seed"]), only_prefix="Qformer")
+    _assert_close(O.qformer_forward(sd, _t(g["query_embeds"]), _t(g["enc"]), d.qf), _t(g["out"]))
+
+
+def test_expert_token_networks(golden):
+    g = golden("networks")
+    sd = syn.make_state_dict(syn.mid_dims(), int(g["seed"]), only_prefix="VE")
+    _, maps = syn.make_inputs(2, seed=int(g["input_seed"]))
+    _assert_close(O.ve_instructor(sd, maps), _t(g["instructor"]))
+    _assert_close(O.ve_tokenizer(sd, maps)[:, :, ::4], _t(g["tokenizer"]))
+    _assert_close(O.conv_stack(sd, "VETokenizer.", maps)[:, ::8], _t(g["trunk_tok"]))
+
+
+def _llama_case(golden, name):
+    g = golden(name)
+    d = syn.tiny_dims(lora_r=int(g["lora_r"]))
+    sd = syn.make_state_dict(d, int(g["seed"]), only_prefix="llama_model")
+    x, mask, labels = _t(g["x"]), _t(g["mask"]), _t(g["labels"])
+    logits, _ = O.llama_logits(sd, x, mask, d)
+    _assert_close(logits, _t(g["logits"]))
+    _assert_close(O.clamp_ce_loss(logits, labels), _t(g["loss"]))
+    toks = O.greedy_generate(sd, x[:, :7].contiguous(), d, 12, ((100,), (101, 102)))
+    assert toks.tolist() == g["greedy_tokens"].tolist()
+
+
+def test_llama_tiny(golden):
+    _llama_case(golden, "llama_tiny")
+
+
+def test_llama_tiny_lora(golden):
+    _llama_case(golden, "llama_tiny_lora")
+
+
+def test_clamp_ce_differs_from_plain_ce_when_clamped():
+    # clamp_CE_loss (modeling_llama.py:718-728) saturates at -log(1e-7); plain CE does not.
+    logits = torch.zeros(1, 2, 4)
+    logits[0, 0, 0] = 60.0
+    labels = torch.tensor([[0, 1]])
+    loss = O.clamp_ce_loss(logits, labels)
+    assert abs(loss.item() - (-np.log(1e-7))) < 1e-3
+
+
+def test_myriad_mid_composite(golden):
+    g = golden("myriad_mid")
+    d = syn.mid_dims()
+    sd = syn.make_state_dict(d, int(g["seed"]))
+    image, maps = syn.make_inputs(2, seed=int(g["input_seed"]))
+    for stage in (0, 1, 2):
+        _assert_close(O.encode_img(sd, image, maps, stage, d)[:, :, ::8], _t(g["encode_stage%d" % stage]))
+    ids_b, ids_a = syn.make_prompt_ids(d.llama.vocab)
+    loss, logits = O.myriad_loss(sd, image, maps, 1, ids_b, ids_a, _t(g["text"]), _t(g["text_mask"]), d)
+    _assert_close(logits[:, ::4, ::5], _t(g["logits_sub"]), 2e-4)
+    _assert_close(loss, _t(g["loss"]), 2e-4)
+    emb = O.prompt_wrap(sd, O.encode_img(sd, image, maps, 1, d), ids_b, ids_a)
+    toks = O.greedy_generate(sd, emb, d, 8)
+    assert toks.tolist() == g["greedy_tokens"].tolist()
