@@ -34,7 +34,7 @@ enum myr_status {
   MYR_ERR_WORKSPACE = -4 /* workspace too small */
 };
 enum myr_dtype { MYR_F16 = 0, MYR_F32 = 1 };
-enum myr_act { MYR_ACT_NONE = 0, MYR_ACT_GELU_ERF = 1 };
+enum myr_act { MYR_ACT_NONE = 0, MYR_ACT_GELU_ERF = 1, MYR_ACT_RELU = 2 };
 
 /* ---- library ------------------------------------------------------------------------------------- */
 int myr_version(void);                            /* ABI version (integer, bumps on breaking change) */
@@ -71,6 +71,93 @@ typedef struct {
 } myr_gemm_args;
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);
 int myr_gemm_f16(const myr_gemm_args* args, void* stream);
+
+/* ---- attention (tcgen05 flash forward) ---------------------------------------------------------------
+ * out[b, i, h, :] = softmax_j(scale * q[b,i,h,:] . k[b,j,h,:] + mask) v[b,j,h,:], fp16 in/out, fp32 softmax.
+ * Replaces eva_vit.py:128-144, Qformer.py:228-265, modeling_llama.py:197-215 (+ the additive masks of
+ * :25-54,442-463, never materialised: key j visible to query i iff j < kv_len[b] and (!causal || j <= q_off + i)).
+ * q/k/v/out are addressed by element strides (token, batch, head), so fused qkv rows and the pre-allocated KV
+ * cache are read in place. All strides and pointers must be 16-byte aligned; dh % 8 == 0, dh <= 128.
+ */
+typedef struct {
+  const void* q; int64_t q_token_stride, q_batch_stride, q_head_stride;
+  const void* k; int64_t k_token_stride, k_batch_stride, k_head_stride;
+  const void* v; int64_t v_token_stride, v_batch_stride, v_head_stride;
+  void* out;     int64_t o_token_stride, o_batch_stride, o_head_stride;
+  int32_t B, H, Sq, Skv, dh;
+  float scale;
+  int32_t causal, q_off;
+  const void* kv_len;      /* int32 [B] device (valid keys per batch row) or NULL = Skv */
+  int32_t bn_hint;         /* keys per tile (multiple of 32), 0 = auto */
+} myr_attn_args;
+int myr_attention_fwd(const myr_attn_args* args, void* stream);
+
+/* ---- LayerNorm / RMSNorm (+ fused LoraAdaptorV2) ----------------------------------------------------
+ * y = norm(x [+ W2 (W1 x)]) * gamma (+ beta); statistics in fp32. Replaces blip2.py:119-125 (ln_vision),
+ * eva_vit.py:173-180 norm1/norm2 (eps 1e-6), Qformer.py LayerNorm (eps 1e-12), modeling_llama.py:66-74 (rms=1),
+ * and with adaptor_w1/w2 set networks.py:81-93 fused in front of ln_vision (myriad.py:248).
+ * x: fp16 or fp32 rows; outputs (each optional): out16 (fp16, GEMM operand), out32 (fp32 residual stream),
+ * pre32 (fp32 pre-norm value), stats [rows, 2] = (mean, rstd). D % 4 == 0, D <= 4096, rank <= 4.
+ */
+typedef struct {
+  const void* x; int32_t x_dtype; int64_t ldx;
+  int32_t rows, D;
+  const void* gamma; const void* beta;     /* fp32 [D]; beta NULL for RMSNorm */
+  float eps; int32_t rms;
+  const void* adaptor_w1; const void* adaptor_w2; int32_t rank; /* fp32 [rank, D], [D, rank] or NULL */
+  void* out16; int64_t ld16;
+  void* out32; int64_t ld32;
+  void* pre32; int64_t ldpre;
+  void* stats;
+} myr_norm_args;
+int myr_norm_fwd(const myr_norm_args* args, void* stream);
+
+/* ---- RoPE + KV-cache append (modeling_llama.py:109-123,190-195) -------------------------------------
+ * qkv: [B*S, 3*H*dh] fp16 fused rows; q is rotated in place, rotated k and v are written to cache slot
+ * cache_off + s of batch row b. cos/sin: fp32 [max_pos, dh/2]. pos: int32 [B*S]. cache_off_dev (device int32
+ * scalar) overrides cache_off when non-NULL (CUDA-graph replay of decode steps).
+ */
+typedef struct {
+  void* qkv; int64_t ldq;
+  int32_t B, S, H, dh;
+  const void* pos;
+  const void* cos_table; const void* sin_table;
+  void* kcache; void* vcache; int64_t cache_token_stride, cache_batch_stride;
+  int32_t cache_off; const void* cache_off_dev;
+} myr_rope_args;
+int myr_rope_cache(const myr_rope_args* args, void* stream);
+
+/* SwiGLU modeling_llama.py:139-140: out[t, i] = silu(gate_up[t, i]) * gate_up[t, I + i] (fp16). */
+int myr_swiglu(const void* gate_up, int64_t ld_gu, void* out, int64_t ld_out, int32_t T, int32_t I, void* stream);
+/* Embedding gather myriad.py:308-311: out[r, :] = table[ids[r], :]; table fp16 [V, D]; ids int32 or int64 (device). */
+int myr_embed(const void* table, int32_t D, const void* ids, int32_t ids_are_int64, int32_t n, void* out,
+              int32_t out_dtype, int64_t ld_out, void* stream);
+/* Strided row copy / cast (places token groups into the concatenated buffers of myriad.py:249-266,372). */
+int myr_copy_rows(const void* src, int32_t src_dtype, int64_t src_ld, int64_t src_group_stride, void* dst,
+                  int32_t dst_dtype, int64_t dst_ld, int64_t dst_group_stride, int32_t groups, int32_t rows_per_group,
+                  int32_t D, void* stream);
+/* ViT token assembly eva_vit.py:326-331: x[b,0] = cls + pos[0]; x[b,1+p] = patch[b,p] + pos[1+p] (fp32). */
+int myr_vit_assemble(const void* patch, const void* cls, const void* pos, void* x, int32_t B, int32_t N, int32_t D,
+                     void* stream);
+/* ViT patchify eva_vit.py:196-203: image fp32 [B,C,HW,HW] -> fp16 [B*g*g, ldp] columns (c, ky, kx), pad zeroed. */
+int myr_patchify(const void* image, void* patches, int32_t B, int32_t C, int32_t HW, int32_t P, int32_t ldp, void* stream);
+
+/* ---- expert-prior conv stacks (networks.py:95-197), NHWC fp16 ---------------------------------------- */
+/* conv3x3(pad 1) + bias + ReLU + maxpool2 fused; in fp32 or fp16 [B,H,W,Cin]; w fp32 [Cout,3,3,Cin]; out fp16. */
+int myr_conv3x3_relu_pool(const void* in, int32_t in_dtype, const void* w, const void* bias, void* out, int32_t B,
+                          int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream);
+/* im2col on NHWC fp16: out [(b,oy,ox), (ky,kx,c)], zero padding `pad`, stride 1. */
+int myr_im2col(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t KH, int32_t KW, int32_t pad,
+               void* stream);
+int myr_maxpool2(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* ---- greedy decoding step (HF generate greedy search + conversation.py:96-107), all state on device ------
+ * state (int32): [0] step [1] done [2] cache_off [3] - | unfinished[B] | cur_tok[B] | kv_len[B] | pos[B] |
+ * tokens[B, max_new_tokens]. scratch: int32 [B]. stop_seqs: int32 [n_stops, stop_max_len], -1 padded.
+ */
+int myr_greedy_step(const void* logits, int64_t ld_logits, int32_t B, int32_t V, void* state, void* scratch,
+                    int32_t max_new_tokens, int32_t min_new_tokens, int32_t eos, const void* stop_seqs, int32_t n_stops,
+                    int32_t stop_max_len, void* stream);
 
 #ifdef __cplusplus
 }

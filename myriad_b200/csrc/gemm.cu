@@ -55,6 +55,7 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& ep, float v, floa
   if (ep.round_acc) v = round_f16(v);
   if (f < ep.scale_cols) v = round_f16(v * ep.scale);
   if (ep.act == MYR_ACT_GELU_ERF) v = round_f16(gelu_erf(v));
+  else if (ep.act == MYR_ACT_RELU) v = fmaxf(v, 0.f);
   if (ep.res) {
     float r = (ep.res_dtype == MYR_F32) ? reinterpret_cast<const float*>(ep.res)[t * ep.ldr + f]
                                         : __half2float(reinterpret_cast<const __half*>(ep.res)[t * ep.ldr + f]);

@@ -93,3 +93,144 @@ def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.floa
     a.bn_hint, a.ksplit_hint = bn_hint, ksplit_hint
     check(lib().myr_gemm_f16(ctypes.byref(a), _stream()), "myr_gemm_f16")
     return out
+
+
+ACT_RELU = 2
+
+
+class AttnArgs(ctypes.Structure):
+    _fields_ = [
+        ("q", ctypes.c_void_p), ("q_ts", ctypes.c_int64), ("q_bs", ctypes.c_int64), ("q_hs", ctypes.c_int64),
+        ("k", ctypes.c_void_p), ("k_ts", ctypes.c_int64), ("k_bs", ctypes.c_int64), ("k_hs", ctypes.c_int64),
+        ("v", ctypes.c_void_p), ("v_ts", ctypes.c_int64), ("v_bs", ctypes.c_int64), ("v_hs", ctypes.c_int64),
+        ("out", ctypes.c_void_p), ("o_ts", ctypes.c_int64), ("o_bs", ctypes.c_int64), ("o_hs", ctypes.c_int64),
+        ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("Sq", ctypes.c_int32), ("Skv", ctypes.c_int32),
+        ("dh", ctypes.c_int32),
+        ("scale", ctypes.c_float),
+        ("causal", ctypes.c_int32), ("q_off", ctypes.c_int32),
+        ("kv_len", ctypes.c_void_p),
+        ("bn_hint", ctypes.c_int32),
+    ]
+
+
+def attention(q, k, v, out, B, H, Sq, Skv, dh, scale, q_strides, k_strides, v_strides, o_strides, causal=False, q_off=0,
+              kv_len=None, bn_hint=0):
+    """Strided flash attention. q/k/v/out: fp16 tensors (any view; only data_ptr is used); *_strides =
+    (token, batch, head) element strides."""
+    a = AttnArgs()
+    a.q, (a.q_ts, a.q_bs, a.q_hs) = q.data_ptr(), q_strides
+    a.k, (a.k_ts, a.k_bs, a.k_hs) = k.data_ptr(), k_strides
+    a.v, (a.v_ts, a.v_bs, a.v_hs) = v.data_ptr(), v_strides
+    a.out, (a.o_ts, a.o_bs, a.o_hs) = out.data_ptr(), o_strides
+    a.B, a.H, a.Sq, a.Skv, a.dh = B, H, Sq, Skv, dh
+    a.scale = scale
+    a.causal, a.q_off = int(causal), q_off
+    a.kv_len = kv_len.data_ptr() if kv_len is not None else None
+    a.bn_hint = bn_hint
+    check(lib().myr_attention_fwd(ctypes.byref(a), _stream()), "myr_attention_fwd")
+    return out
+
+
+class NormArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("x_dtype", ctypes.c_int32), ("ldx", ctypes.c_int64),
+        ("rows", ctypes.c_int32), ("D", ctypes.c_int32),
+        ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+        ("eps", ctypes.c_float), ("rms", ctypes.c_int32),
+        ("w1", ctypes.c_void_p), ("w2", ctypes.c_void_p), ("rank", ctypes.c_int32),
+        ("out16", ctypes.c_void_p), ("ld16", ctypes.c_int64),
+        ("out32", ctypes.c_void_p), ("ld32", ctypes.c_int64),
+        ("pre32", ctypes.c_void_p), ("ldpre", ctypes.c_int64),
+        ("stats", ctypes.c_void_p),
+    ]
+
+
+def norm(x, gamma, beta, eps, rms=False, out16=None, out32=None, w1=None, w2=None, pre32=None, stats=None):
+    """x: [rows, D] fp16/fp32 (row stride free). gamma/beta/w1/w2 fp32."""
+    rows, D = x.shape
+    a = NormArgs()
+    a.x, a.x_dtype, a.ldx = x.data_ptr(), _dt(x), x.stride(0)
+    a.rows, a.D = rows, D
+    assert gamma.dtype == torch.float32 and (beta is None or beta.dtype == torch.float32)
+    a.gamma, a.beta = gamma.data_ptr(), (beta.data_ptr() if beta is not None else None)
+    a.eps, a.rms = eps, int(rms)
+    if w1 is not None:
+        assert w1.dtype == torch.float32 and w2.dtype == torch.float32 and w1.is_contiguous() and w2.is_contiguous()
+        a.w1, a.w2, a.rank = w1.data_ptr(), w2.data_ptr(), w1.shape[0]
+    for name, t, ld, dt in (("out16", out16, "ld16", torch.float16), ("out32", out32, "ld32", torch.float32),
+                            ("pre32", pre32, "ldpre", torch.float32)):
+        if t is not None:
+            assert t.dtype == dt and t.stride(-1) == 1
+            setattr(a, name, t.data_ptr())
+            setattr(a, ld, t.stride(0))
+    a.stats = stats.data_ptr() if stats is not None else None
+    check(lib().myr_norm_fwd(ctypes.byref(a), _stream()), "myr_norm_fwd")
+
+
+class RopeArgs(ctypes.Structure):
+    _fields_ = [
+        ("qkv", ctypes.c_void_p), ("ldq", ctypes.c_int64),
+        ("B", ctypes.c_int32), ("S", ctypes.c_int32), ("H", ctypes.c_int32), ("dh", ctypes.c_int32),
+        ("pos", ctypes.c_void_p),
+        ("cos", ctypes.c_void_p), ("sin", ctypes.c_void_p),
+        ("kcache", ctypes.c_void_p), ("vcache", ctypes.c_void_p), ("c_ts", ctypes.c_int64), ("c_bs", ctypes.c_int64),
+        ("cache_off", ctypes.c_int32), ("cache_off_dev", ctypes.c_void_p),
+    ]
+
+
+def rope_cache(qkv, B, S, H, dh, pos, cos, sin, kcache, vcache, cache_off=0, cache_off_dev=None):
+    a = RopeArgs()
+    a.qkv, a.ldq = qkv.data_ptr(), qkv.stride(0)
+    a.B, a.S, a.H, a.dh = B, S, H, dh
+    assert pos.dtype == torch.int32
+    a.pos, a.cos, a.sin = pos.data_ptr(), cos.data_ptr(), sin.data_ptr()
+    a.kcache, a.vcache = kcache.data_ptr(), vcache.data_ptr()
+    a.c_ts, a.c_bs = kcache.stride(1), kcache.stride(0)
+    a.cache_off = cache_off
+    a.cache_off_dev = cache_off_dev.data_ptr() if cache_off_dev is not None else None
+    check(lib().myr_rope_cache(ctypes.byref(a), _stream()), "myr_rope_cache")
+
+
+def _i64(v):
+    return ctypes.c_int64(v)
+
+
+def swiglu(gate_up, out, T, I):
+    check(lib().myr_swiglu(_p(gate_up), _i64(gate_up.stride(0)), _p(out), _i64(out.stride(0)), T, I, _stream()), "myr_swiglu")
+
+
+def embed(table, ids, out):
+    assert table.dtype == torch.float16 and ids.dtype in (torch.int32, torch.int64)
+    check(lib().myr_embed(_p(table), table.shape[1], _p(ids), int(ids.dtype == torch.int64), ids.numel(), _p(out), _dt(out),
+                          _i64(out.stride(0)), _stream()), "myr_embed")
+
+
+def copy_rows(src, dst, groups, rows_per_group, D, src_ld, src_gs, dst_ld, dst_gs):
+    check(lib().myr_copy_rows(_p(src), _dt(src), _i64(src_ld), _i64(src_gs), _p(dst), _dt(dst), _i64(dst_ld), _i64(dst_gs),
+                              groups, rows_per_group, D, _stream()), "myr_copy_rows")
+
+
+def vit_assemble(patch, cls, pos, x, B, N, D):
+    check(lib().myr_vit_assemble(_p(patch), _p(cls), _p(pos), _p(x), B, N, D, _stream()), "myr_vit_assemble")
+
+
+def patchify(image, patches, B, C, HW, P):
+    check(lib().myr_patchify(_p(image), _p(patches), B, C, HW, P, patches.stride(0), _stream()), "myr_patchify")
+
+
+def conv3x3_relu_pool(x, w, bias, out, B, H, W, Cin, Cout):
+    check(lib().myr_conv3x3_relu_pool(_p(x), _dt(x), _p(w), _p(bias), _p(out), B, H, W, Cin, Cout, _stream()),
+          "myr_conv3x3_relu_pool")
+
+
+def im2col(x, out, B, H, W, C, KH, KW, pad):
+    check(lib().myr_im2col(_p(x), _p(out), B, H, W, C, KH, KW, pad, _stream()), "myr_im2col")
+
+
+def maxpool2(x, out, B, H, W, C):
+    check(lib().myr_maxpool2(_p(x), _p(out), B, H, W, C, _stream()), "myr_maxpool2")
+
+
+def greedy_step(logits, state, scratch, B, V, max_new, min_new, eos, stops, n_stops, stop_max_len):
+    check(lib().myr_greedy_step(_p(logits), _i64(logits.stride(0)), B, V, _p(state), _p(scratch), max_new, min_new, eos,
+                                _p(stops), n_stops, stop_max_len, _stream()), "myr_greedy_step")
