@@ -68,6 +68,8 @@ typedef struct {
   void* workspace; size_t workspace_bytes;         /* split-K partials; see myr_gemm_workspace_bytes */
   int32_t bn_hint;             /* token tile (multiple of 16, <= 256), 0 = auto */
   int32_t ksplit_hint;         /* 0 = auto */
+  int32_t out_group_rows;      /* 0 = plain; else out row t is stored at (t / rows) * out_group_stride + (t % rows) * ldo: */
+  int64_t out_group_stride;    /*   writes token groups straight into a concatenated [B, L, F] buffer (myriad.py:249-266) */
 } myr_gemm_args;
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);
 int myr_gemm_f16(const myr_gemm_args* args, void* stream);

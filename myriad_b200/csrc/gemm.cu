@@ -38,6 +38,8 @@ struct Epilogue {
   void* out;
   int out_dtype;
   long long ldo;
+  int group_rows;          // 0 = plain rows; else out row t lives at (t / group_rows) * group_stride + (t % group_rows) * ldo
+  long long group_stride;
 };
 
 struct GemmKernelParams {
@@ -61,10 +63,12 @@ __device__ __forceinline__ void epilogue_store(const Epilogue& ep, float v, floa
                                         : __half2float(reinterpret_cast<const __half*>(ep.res)[t * ep.ldr + f]);
     v += r;
   }
+  const long long o = ep.group_rows ? (t / ep.group_rows) * ep.group_stride + (t % ep.group_rows) * ep.ldo + f
+                                    : t * ep.ldo + f;
   if (ep.out_dtype == MYR_F32)
-    reinterpret_cast<float*>(ep.out)[t * ep.ldo + f] = v;
+    reinterpret_cast<float*>(ep.out)[o] = v;
   else
-    reinterpret_cast<__half*>(ep.out)[t * ep.ldo + f] = __float2half_rn(v);
+    reinterpret_cast<__half*>(ep.out)[o] = __float2half_rn(v);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -384,6 +388,7 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   p.ep.scale_cols = a->scale_cols; p.ep.scale = a->scale;
   p.ep.res = a->res; p.ep.res_dtype = a->res_dtype; p.ep.ldr = a->ldr;
   p.ep.out = a->out; p.ep.out_dtype = a->out_dtype; p.ep.ldo = a->ldo;
+  p.ep.group_rows = a->out_group_rows; p.ep.group_stride = a->out_group_stride;
 
   const size_t smem_bytes = (size_t)pl.num_stages * pl.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;

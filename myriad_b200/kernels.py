@@ -41,6 +41,7 @@ class GemmArgs(ctypes.Structure):
         ("out", ctypes.c_void_p), ("out_dtype", ctypes.c_int32), ("ldo", ctypes.c_int64),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("bn_hint", ctypes.c_int32), ("ksplit_hint", ctypes.c_int32),
+        ("out_group_rows", ctypes.c_int32), ("out_group_stride", ctypes.c_int64),
     ]
 
 
@@ -58,7 +59,8 @@ def workspace(nbytes, device):
 
 
 def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.float16, scale_cols=0, scale=1.0,
-         round_acc=False, x_mn_major=False, w_mn_major=False, T=None, F=None, K=None, bn_hint=0, ksplit_hint=0):
+         round_acc=False, x_mn_major=False, w_mn_major=False, T=None, F=None, K=None, bn_hint=0, ksplit_hint=0,
+         out_group_rows=0, out_group_stride=0, ldo=None):
     """out[t, f] = epilogue(sum_k x[t, k] * w[f, k]);  x: [T, K] fp16 (row stride may exceed K), w: [F, K] fp16."""
     assert x.dtype == torch.float16 and w.dtype == torch.float16
     assert x.stride(-1) == 1 and w.stride(-1) == 1
@@ -88,9 +90,11 @@ def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.floa
     else:
         a.res, a.res_dtype, a.ldr = None, 0, 0
     assert out.stride(-1) == 1
-    a.out, a.out_dtype, a.ldo = out.data_ptr(), _dt(out), out.stride(0)
+    a.out, a.out_dtype, a.ldo = out.data_ptr(), _dt(out), (ldo if ldo is not None else out.stride(0))
+    assert out.dim() == 2 or ldo is not None, "flat output needs an explicit row stride"
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     a.bn_hint, a.ksplit_hint = bn_hint, ksplit_hint
+    a.out_group_rows, a.out_group_stride = out_group_rows, out_group_stride
     check(lib().myr_gemm_f16(ctypes.byref(a), _stream()), "myr_gemm_f16")
     return out
 
