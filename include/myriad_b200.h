@@ -40,6 +40,7 @@ enum myr_act { MYR_ACT_NONE = 0, MYR_ACT_GELU_ERF = 1, MYR_ACT_RELU = 2 };
 int myr_version(void);                            /* ABI version (integer, bumps on breaking change) */
 int myr_last_error(char* buf, size_t buf_bytes);  /* copies last error message of calling thread */
 int myr_device_sm_count(void);
+unsigned long long myr_launch_count(void);        /* kernels launched (or captured into a CUDA graph) by this library */
 
 /* ---- GEMM (tcgen05 + TMA) --------------------------------------------------------------------------
  * out[t, f] = epilogue( sum_k X[t, k] * W[f, k] )          t < T tokens, f < F features

@@ -25,6 +25,7 @@ def lib():
         _lib.myr_version.restype = ctypes.c_int
         _lib.myr_last_error.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         _lib.myr_device_sm_count.restype = ctypes.c_int
+        _lib.myr_launch_count.restype = ctypes.c_ulonglong
     return _lib
 
 

@@ -13,6 +13,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -84,4 +87,6 @@ int myr_last_error(char* buf, size_t n) {
 }
 
 int myr_device_sm_count(void) { return myr::sm_count(); }
+
+unsigned long long myr_launch_count(void) { return __atomic_load_n(&myr::g_launches, __ATOMIC_RELAXED); }
 }

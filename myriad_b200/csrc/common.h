@@ -11,6 +11,7 @@
 namespace myr {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 int sm_count();
 
 // cuTensorMapEncodeTiled obtained through the runtime (no link-time libcuda dependency).
@@ -35,7 +36,12 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
     }                                                                                          \
   } while (0)
 
-#define MYR_CHECK_LAUNCH() MYR_CHECK_CUDA(cudaGetLastError())
+// every kernel launch in the library is followed by this macro: it also feeds myr_launch_count()
+#define MYR_CHECK_LAUNCH()                \
+  do {                                    \
+    myr::count_launch();                  \
+    MYR_CHECK_CUDA(cudaGetLastError());   \
+  } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

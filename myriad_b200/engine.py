@@ -424,11 +424,14 @@ class MyriadEngine:
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     st.state.copy_(snap)
+                    n0 = K.launch_count()
                     with torch.cuda.graph(g):
                         self._decode_step(st)
+                    st.graph_nodes = K.launch_count() - n0
                     st.graph = g
                     st.state.copy_(snap)  # capture does not execute; replay from the snapshot
                 st.graph.replay()
+                K.note_graph_replay(st.graph_nodes)
             else:
                 self._decode_step(st)
         n = int(st.state[0].item())
@@ -438,21 +441,33 @@ class MyriadEngine:
     # ----------------------------------------------------------------------------------------- generate
     def build_inputs_embeds(self, image, maps, stage, ids_before, ids_after, with_bos=False, text_ids=None):
         """prompt_wrap myriad.py:354-375 (+ bos / target-text embeds of Myriad.forward :395-421): writes
-        [bos] + before + image tokens + after [+ text] straight into one fp32 [B, L, D] buffer."""
+        [bos] + before + image tokens + after [+ text] straight into one fp32 [B, L, D] buffer.
+        ids_before / ids_after: int64 [n] (shared by the batch) or [B, n] (per sample; equal lengths, as the
+        reference's torch.stack at myriad.py:371 requires)."""
         l, dev = self.d.llama, self.dev
         B, D = image.shape[0], l.hidden
         n_img = self.num_image_tokens(stage)
-        nb, na = ids_before.numel(), ids_after.numel()
+        ids_before, ids_after = ids_before.long().cpu(), ids_after.long().cpu()
+        shared = ids_before.dim() == 1
+        if shared:
+            ids_before, ids_after = ids_before[None], ids_after[None]
+        G = ids_before.shape[0]
+        assert G in (1, B) and ids_after.shape[0] == G
+        nb, na = ids_before.shape[1], ids_after.shape[1]
         n0 = 1 if with_bos else 0
         nt = 0 if text_ids is None else text_ids.shape[1]
         L = n0 + nb + n_img + na + nt
         buf = torch.empty(B, L, D, device=dev, dtype=F32)
         flat = buf.reshape(-1)
-        head = torch.cat(([torch.tensor([l.bos])] if with_bos else []) + [ids_before.cpu().long()]).to(dev)
-        tmp = torch.empty(head.numel() + na, D, device=dev, dtype=F32)
-        K.embed(self.llw.embed, torch.cat([head, ids_after.to(dev).long()]), tmp)
-        K.copy_rows(tmp, flat, B, n0 + nb, D, D, 0, D, L * D)
-        K.copy_rows(tmp[n0 + nb:], flat[(n0 + nb + n_img) * D:], B, na, D, D, 0, D, L * D)
+        head = torch.cat([torch.full((G, n0), l.bos, dtype=torch.long), ids_before, ids_after], 1)  # [G, n0+nb+na]
+        nh = head.shape[1]
+        tmp = torch.empty(G * nh, D, device=dev, dtype=F32)
+        K.embed(self.llw.embed, head.reshape(-1).to(dev), tmp)
+        gs = 0 if G == 1 else nh * D
+        if n0 + nb:
+            K.copy_rows(tmp, flat, B, n0 + nb, D, D, gs, D, L * D)
+        if na:
+            K.copy_rows(tmp[n0 + nb:], flat[(n0 + nb + n_img) * D:], B, na, D, D, gs, D, L * D)
         self.encode_img(image, maps, stage, out=flat[(n0 + nb) * D:], out_batch_stride=L * D)
         if nt:
             tt = torch.empty(B * nt, D, device=dev, dtype=F32)

@@ -238,3 +238,16 @@ def maxpool2(x, out, B, H, W, C):
 def greedy_step(logits, state, scratch, B, V, max_new, min_new, eos, stops, n_stops, stop_max_len):
     check(lib().myr_greedy_step(_p(logits), _i64(logits.stride(0)), B, V, _p(state), _p(scratch), max_new, min_new, eos,
                                 _p(stops), n_stops, stop_max_len, _stream()), "myr_greedy_step")
+
+
+_graph_replay_launches = 0
+
+
+def launch_count():
+    """Kernels of this library launched so far in this process: eager launches + (nodes captured) x (graph replays)."""
+    return int(lib().myr_launch_count()) + _graph_replay_launches
+
+
+def note_graph_replay(n_nodes):
+    global _graph_replay_launches
+    _graph_replay_launches += n_nodes

@@ -224,3 +224,31 @@ def make_prompt_ids(vocab, n_before=6, n_after=26, seed=7):
     g.manual_seed(seed)
     ids = torch.randint(3, vocab, (n_before + n_after,), generator=g)
     return ids[:n_before].clone(), ids[n_before:].clone()
+
+
+class LazyStateDict:
+    """Mapping view of make_state_dict that materialises one tensor per lookup (7 B parameters never sit in memory
+    twice). Used by the benchmarks at full size; tests use the eager dict so the oracle sees the same tensors."""
+
+    def __init__(self, d: MyriadDims, seed=0, device="cpu"):
+        self._spec = {k: (shape, std, mean) for k, shape, std, mean in state_dict_spec(d)}
+        self._seed, self._device = seed, device
+
+    def __getitem__(self, key):
+        shape, std, mean = self._spec[key]
+        return synth(key, shape, std, self._seed, device=self._device, mean=mean)
+
+    def __contains__(self, key):
+        return key in self._spec
+
+    def keys(self):
+        return self._spec.keys()
+
+    def num_parameters(self):
+        n = 0
+        for shape, _, _ in self._spec.values():
+            m = 1
+            for s in shape:
+                m *= s
+            n += m
+        return n
