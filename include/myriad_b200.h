@@ -52,8 +52,8 @@ unsigned long long myr_launch_count(void);        /* kernels launched (or captur
  *   x_mn_major / w_mn_major = 0: operand stored [rows, K] (K contiguous, nn.Linear layout);
  *                           = 1: operand stored [K, rows] (rows contiguous) — used by dgrad/wgrad.
  * Epilogue order (each step optional): v = acc (+ bias[f]); if round_acc: v = fp16(v);
- *   if f < scale_cols: v = fp16(v * scale); if act: v = fp16(act(v)); if res: v += res[t, f]; store as out_dtype.
- * Alignment: x, w, out 16-byte aligned; ldx, ldw multiples of 8 elements; K multiple of 8.
+ *   if f < scale_cols: v = fp16(v * scale); if act: v = fp16(act(v)); v *= alpha; if res: v += res[t, f]; store as out_dtype.
+ * Alignment: x, w, out 16-byte aligned; ldx, ldw (and batch strides) multiples of 8 elements.
  */
 typedef struct {
   const void* x; int64_t ldx;
@@ -71,6 +71,9 @@ typedef struct {
   int32_t ksplit_hint;         /* 0 = auto */
   int32_t out_group_rows;      /* 0 = plain; else out row t is stored at (t / rows) * out_group_stride + (t % rows) * ldo: */
   int64_t out_group_stride;    /*   writes token groups straight into a concatenated [B, L, F] buffer (myriad.py:249-266) */
+  int32_t nb0, nb1;            /* batched GEMM over nb0 x nb1 independent problems (0 = 1): attention backward per (batch, head) */
+  int64_t x_bs0, x_bs1, w_bs0, w_bs1, o_bs0, o_bs1; /* element strides of the two batch dims; no residual / split-K when batched */
+  int32_t alpha_set; float alpha; /* if alpha_set: v *= alpha (fp32, unrounded) after the activation, before the residual add */
 } myr_gemm_args;
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);
 int myr_gemm_f16(const myr_gemm_args* args, void* stream);
@@ -161,6 +164,60 @@ int myr_maxpool2(const void* in, void* out, int32_t B, int32_t H, int32_t W, int
 int myr_greedy_step(const void* logits, int64_t ld_logits, int32_t B, int32_t V, void* state, void* scratch,
                     int32_t max_new_tokens, int32_t min_new_tokens, int32_t eos, const void* stop_seqs, int32_t n_stops,
                     int32_t stop_max_len, void* stream);
+
+/* ==== training (backward) entry points =================================================================
+ * Gradients flow loss -> lm_head -> 32 LLaMA layers -> inputs_embeds -> {VETokenizer, base_prompts, llama_proj ->
+ * Q-Former -> {VEInstructor, ln_vision -> LoraAdaptorV2}} (everything else is frozen: dgrad only). Matrix products
+ * reuse myr_gemm_f16 with MN-major operands; attention backward = batched myr_gemm_f16 around the two softmax kernels.
+ */
+/* clamp_CE_loss modeling_llama.py:718-728 on [R, V] fp32 logits, labels int64 [R] (-100 = ignored).
+ * fwd: row_loss [R], stats [R,2] = (max, sumexp), loss_out[2] = (mean loss, #supervised rows).
+ * bwd: dlogits fp16 [R, V] = loss_scale / count * (softmax - onehot), zero where p_y is clamped or the row ignored. */
+int myr_clamp_ce_fwd(const void* logits, int64_t ld, int32_t R, int32_t V, const void* labels, void* row_loss, void* stats,
+                     void* loss_out, void* stream);
+int myr_clamp_ce_bwd(const void* logits, int64_t ld, int32_t R, int32_t V, const void* labels, const void* stats,
+                     const void* loss_out, float loss_scale, void* dlogits, int64_t ldd, void* stream);
+/* LayerNorm / RMSNorm input gradient (frozen gamma/beta): x fp32 pre-norm rows, dy fp16|fp32, out = dx (+ add). */
+int myr_norm_bwd(const void* x, int64_t ldx, const void* dy, int32_t dy_dtype, int64_t lddy, const void* gamma, float eps,
+                 int32_t rms, int32_t rows, int32_t D, const void* add, int64_t ldadd, void* out32, int64_t ldo, void* out16,
+                 int64_t ldo16, void* stream);
+int myr_swiglu_bwd(const void* gate_up, int64_t ld_gu, const void* dact, int64_t ld_da, void* dgu, int64_t ld_dgu, int32_t T,
+                   int32_t I, void* stream);
+int myr_gelu_fwd(const void* pre, void* out, int64_t n, void* stream);
+int myr_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, void* stream);
+int myr_rope_bwd(void* dqkv, int64_t ld, int32_t T, int32_t H, int32_t dh, const void* pos, const void* cos_table,
+                 const void* sin_table, void* stream);
+/* P = softmax(scale * S + mask) on materialised score rows [B*H*Sq, cols] (fp32 -> fp16); dS = scale * P * (dP - sum dP P). */
+int myr_softmax_rows(const void* S, int64_t lds, void* P, int64_t ldp, int32_t B, int32_t H, int32_t Sq, int32_t Skv, int32_t cols,
+                     float scale, int32_t causal, const void* kv_len, void* stream);
+int myr_softmax_bwd_rows(const void* P, int64_t ldp, const void* dP, int64_t lddp, void* dS, int64_t lds, int64_t n_rows,
+                         int32_t cols, float scale, void* stream);
+/* dst[r] = src[idx[r]] (scatter = 0) or dst[idx[r]] = src[r] (scatter = 1), with dtype cast; idx int32 device. */
+int myr_index_rows(const void* src, int32_t src_dtype, int64_t src_ld, void* dst, int32_t dst_dtype, int64_t dst_ld,
+                   const void* idx, int32_t R, int32_t D, int32_t scatter, void* stream);
+/* out[c] (+)= scale * sum over groups x rows of src (bias and base_prompts gradients), deterministic. */
+int myr_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_t group_stride, int32_t groups, int32_t rows, int32_t D,
+               float scale, void* out, int32_t accumulate, void* stream);
+/* LoraAdaptorV2 (networks.py:81-93) weight gradients; scratch fp32 [rows, 2*rank]. */
+int myr_adaptor_bwd(const void* x, const void* dy, const void* w1, const void* w2, void* scratch, void* dw1, void* dw2,
+                    int32_t rows, int32_t D, int32_t rank, float scale, void* stream);
+/* fused AdamW over flat fp32 buffers (runner_base.py:105-139), gradient unscale + inf/nan skip (GradScaler) folded in. */
+int myr_adamw_step(void* params, const void* grads, void* exp_avg, void* exp_avg_sq, const void* wd_mask, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float inv_scale, void* found_inf,
+                   void* stream);
+int myr_memset_zero(void* ptr, size_t bytes, void* stream);
+/* conv stacks, training side (networks.py:98-127,159-188): unfused conv+ReLU keeping the pre-pool map, pool+ReLU backward,
+ * direct wgrad (+bias) / dgrad for small channel counts, col2im for the im2col/GEMM layers. NHWC, w [Cout,3,3,Cin] fp32. */
+int myr_conv3x3_relu(const void* in, int32_t in_dtype, const void* w, const void* bias, void* out, int32_t B, int32_t H, int32_t W,
+                     int32_t Cin, int32_t Cout, void* stream);
+int myr_pool_relu_bwd(const void* y, const void* dpool, int32_t dpool_dtype, void* dy, int32_t B, int32_t H, int32_t W, int32_t C,
+                      void* stream);
+int myr_conv3x3_wgrad(const void* in, int32_t in_dtype, const void* dy, void* dw, void* db, int32_t B, int32_t H, int32_t W,
+                      int32_t Cin, int32_t Cout, float scale, void* stream);
+int myr_conv3x3_dgrad(const void* dy, const void* w, void* din, int32_t B, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                      void* stream);
+int myr_col2im(const void* dcols, void* din, int32_t B, int32_t H, int32_t W, int32_t C, int32_t KH, int32_t KW, int32_t pad,
+               void* stream);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,23 @@ __global__ void maxpool2_kernel(const __half* __restrict__ in, __half* __restric
   }
 }
 
+__global__ void maxpool2_scalar_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int H, int W, int C) {
+  const int OH = H >> 1, OW = W >> 1;
+  const long long total = (long long)B * OH * OW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int px = (int)(r % OW);
+    r /= OW;
+    const int py = (int)(r % OH);
+    const int b = (int)(r / OH);
+    const __half* p00 = in + ((size_t)(b * H + 2 * py) * W + 2 * px) * C + c;
+    const float m = fmaxf(fmaxf(__half2float(p00[0]), __half2float(p00[C])),
+                          fmaxf(__half2float(p00[(size_t)W * C]), __half2float(p00[(size_t)W * C + C])));
+    out[i] = __float2half_rn(m);
+  }
+}
+
 // ViT patchify (PatchEmbed conv 14x14 stride 14 as a GEMM, eva_vit.py:196-203): image fp32 NCHW ->
 // patches fp16 [B * g * g, ldp], column order (c, ky, kx) == proj.weight.reshape(D, 3 * P * P); pad columns zeroed.
 __global__ void patchify_kernel(const float* __restrict__ img, __half* __restrict__ out, int B, int C, int HW, int P,
@@ -159,10 +176,16 @@ extern "C" int myr_im2col(const void* in, void* out, int32_t B, int32_t H, int32
 
 extern "C" int myr_maxpool2(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  MYR_CHECK_ARG(in && out && B > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool2: bad arguments");
-  const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
-  maxpool2_kernel<<<ew_grid2(total, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out),
-                                                           B, H, W, C);
+  MYR_CHECK_ARG(in && out && B > 0 && H % 2 == 0 && W % 2 == 0 && C > 0, "maxpool2: bad arguments");
+  if (C % 8 == 0) {
+    const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+    maxpool2_kernel<<<ew_grid2(total, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out),
+                                                             B, H, W, C);
+  } else {
+    const long long total = (long long)B * (H / 2) * (W / 2) * C;
+    maxpool2_scalar_kernel<<<ew_grid2(total, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(in),
+                                                                    reinterpret_cast<__half*>(out), B, H, W, C);
+  }
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }

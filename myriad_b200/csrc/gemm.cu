@@ -38,6 +38,7 @@ struct Epilogue {
   void* out;
   int out_dtype;
   long long ldo;
+  float alpha;             // fp32 scale applied after the activation, before the residual (gradient unscale, LoRA alpha/r)
   int group_rows;          // 0 = plain rows; else out row t lives at (t / group_rows) * group_stride + (t % group_rows) * ldo
   long long group_stride;
 };
@@ -49,22 +50,26 @@ struct GemmKernelParams {
   int x_mn, w_mn;
   uint32_t idesc;
   float* partial;  // [ksplit][T][F] fp32 when ksplit > 1
+  int nb1, nbatch;                 // batched mode: batch index bidx -> (b0 = bidx / nb1, b1 = bidx % nb1)
+  long long o_bs0, o_bs1;          // output element strides of the two batch dims
   Epilogue ep;
 };
 
-__device__ __forceinline__ void epilogue_store(const Epilogue& ep, float v, float bias_f, long long t, int f) {
+__device__ __forceinline__ void epilogue_store(const Epilogue& ep, float v, float bias_f, long long t, int f,
+                                               long long boff = 0) {
   v += bias_f;
   if (ep.round_acc) v = round_f16(v);
   if (f < ep.scale_cols) v = round_f16(v * ep.scale);
   if (ep.act == MYR_ACT_GELU_ERF) v = round_f16(gelu_erf(v));
   else if (ep.act == MYR_ACT_RELU) v = fmaxf(v, 0.f);
+  v *= ep.alpha;
   if (ep.res) {
     float r = (ep.res_dtype == MYR_F32) ? reinterpret_cast<const float*>(ep.res)[t * ep.ldr + f]
                                         : __half2float(reinterpret_cast<const __half*>(ep.res)[t * ep.ldr + f]);
     v += r;
   }
-  const long long o = ep.group_rows ? (t / ep.group_rows) * ep.group_stride + (t % ep.group_rows) * ep.ldo + f
-                                    : t * ep.ldo + f;
+  const long long o = boff + (ep.group_rows ? (t / ep.group_rows) * ep.group_stride + (t % ep.group_rows) * ep.ldo + f
+                                            : t * ep.ldo + f);
   if (ep.out_dtype == MYR_F32)
     reinterpret_cast<float*>(ep.out)[o] = v;
   else
@@ -107,7 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int units = p.n_tt * p.n_ft * p.ksplit;
+  const int units = p.n_tt * p.n_ft * p.ksplit * p.nbatch;
   const uint32_t tx_bytes = A_STAGE_BYTES + p.BN * BK * 2;
 
   if (warp == 0) {
@@ -118,7 +123,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int tt = u % p.n_tt;
         const int ft = (u / p.n_tt) % p.n_ft;
-        const int ks = u / (p.n_tt * p.n_ft);
+        const int ks = (u / (p.n_tt * p.n_ft)) % p.ksplit;
+        const int bidx = u / (p.n_tt * p.n_ft * p.ksplit);
+        const int b0 = bidx / p.nb1, b1 = bidx % p.nb1;
         const int f0 = ft * BM, t0 = tt * p.BN;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -128,15 +135,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           uint8_t* sb = sa + A_STAGE_BYTES;
           mbar_arrive_expect_tx(&full[stage], tx_bytes);
           if (!p.w_mn) {
-            tma_load_2d(sa, &tmW, &full[stage], kb * BK, f0);
+            tma_load_4d(sa, &tmW, &full[stage], kb * BK, f0, b1, b0);
           } else {
-            tma_load_2d(sa, &tmW, &full[stage], f0, kb * BK);
-            tma_load_2d(sa + 8192, &tmW, &full[stage], f0 + 64, kb * BK);
+            tma_load_4d(sa, &tmW, &full[stage], f0, kb * BK, b1, b0);
+            tma_load_4d(sa + 8192, &tmW, &full[stage], f0 + 64, kb * BK, b1, b0);
           }
           if (!p.x_mn) {
-            tma_load_2d(sb, &tmX, &full[stage], kb * BK, t0);
+            tma_load_4d(sb, &tmX, &full[stage], kb * BK, t0, b1, b0);
           } else {
-            for (int i = 0; i < p.BN / 64; ++i) tma_load_2d(sb + i * 8192, &tmX, &full[stage], t0 + 64 * i, kb * BK);
+            for (int i = 0; i < p.BN / 64; ++i) tma_load_4d(sb + i * 8192, &tmX, &full[stage], t0 + 64 * i, kb * BK, b1, b0);
           }
           if (++stage == p.num_stages) {
             stage = 0;
@@ -155,7 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       const uint32_t a_lbo = p.w_mn ? 8192 : 16, b_lbo = p.x_mn ? 8192 : 16;
       const uint32_t a_kstep = p.w_mn ? 2048 : 32, b_kstep = p.x_mn ? 2048 : 32;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int ks = u / (p.n_tt * p.n_ft);
+        const int ks = (u / (p.n_tt * p.n_ft)) % p.ksplit;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -193,7 +200,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int tt = u % p.n_tt;
       const int ft = (u / p.n_tt) % p.n_ft;
-      const int ks = u / (p.n_tt * p.n_ft);
+      const int ks = (u / (p.n_tt * p.n_ft)) % p.ksplit;
+      const int bidx = u / (p.n_tt * p.n_ft * p.ksplit);
+      const long long boff = (long long)(bidx / p.nb1) * p.o_bs0 + (long long)(bidx % p.nb1) * p.o_bs1;
       const int f = ft * BM + q * 32 + lane;
       const int t0 = tt * p.BN;
       mbar_wait(&tfull[as], aphase);
@@ -214,7 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             if (t < p.T) {
               const float v = __uint_as_float(r[j]);
               if (p.ksplit == 1)
-                epilogue_store(p.ep, v, bias_f, t, f);
+                epilogue_store(p.ep, v, bias_f, t, f, boff);
               else
                 p.partial[((long long)ks * p.T + t) * p.F + f] = v;
             }
@@ -329,7 +338,11 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MYR_CHECK_ARG(a != nullptr, "gemm: null args");
   MYR_CHECK_ARG(a->T > 0 && a->F > 0 && a->K > 0, "gemm: bad shape T=%d F=%d K=%d", a->T, a->F, a->K);
-  MYR_CHECK_ARG(a->K % 8 == 0, "gemm: K=%d must be a multiple of 8", a->K);
+  const int nb0 = a->nb0 > 0 ? a->nb0 : 1, nb1 = a->nb1 > 0 ? a->nb1 : 1;
+  const int nbatch = nb0 * nb1;
+  MYR_CHECK_ARG(nbatch == 1 || (a->res == nullptr && a->out_group_rows == 0), "gemm: batched mode supports no residual / row groups");
+  MYR_CHECK_ARG(a->x_bs0 % 8 == 0 && a->x_bs1 % 8 == 0 && a->w_bs0 % 8 == 0 && a->w_bs1 % 8 == 0,
+                "gemm: batch strides must be multiples of 8 elements");
   MYR_CHECK_ARG(a->ldx % 8 == 0 && a->ldw % 8 == 0, "gemm: ldx=%lld ldw=%lld must be multiples of 8", (long long)a->ldx,
                 (long long)a->ldw);
   MYR_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
@@ -338,10 +351,8 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   MYR_CHECK_ARG(a->bn_hint == 0 || (a->bn_hint % 16 == 0 && a->bn_hint >= 16 && a->bn_hint <= 256),
                 "gemm: bn_hint=%d must be a multiple of 16 in [16,256]", a->bn_hint);
   MYR_CHECK_ARG(!a->x_mn_major || a->bn_hint % 64 == 0, "gemm: MN-major x needs bn_hint multiple of 64");
-  MYR_CHECK_ARG(!a->x_mn_major || a->T % 8 == 0, "gemm: MN-major x needs T multiple of 8");
-  MYR_CHECK_ARG(!a->w_mn_major || a->F % 8 == 0, "gemm: MN-major w needs F multiple of 8");
 
-  Plan pl = make_plan(a->T, a->F, a->K, a->x_mn_major, a->bn_hint, a->ksplit_hint);
+  Plan pl = make_plan(a->T, a->F, a->K, a->x_mn_major, a->bn_hint, nbatch > 1 ? 1 : a->ksplit_hint);
   if (pl.ksplit > 1) {
     const size_t need = (size_t)pl.ksplit * a->T * a->F * sizeof(float);
     if (a->workspace == nullptr || a->workspace_bytes < need) {
@@ -355,15 +366,18 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
 
   CUtensorMap tmW, tmX;
   {
-    uint64_t dims[2], strides[1];
-    uint32_t box[2];
+    uint64_t dims[4], strides[3];
+    uint32_t box[4];
+    dims[2] = (uint64_t)nb1; dims[3] = (uint64_t)nb0; box[2] = 1; box[3] = 1;
     if (!a->w_mn_major) {
       dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)a->F; box[0] = BK; box[1] = BM;
     } else {
       dims[0] = (uint64_t)a->F; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
     }
     strides[0] = (uint64_t)a->ldw * 2;
-    int rc = make_tmap_f16(&tmW, a->w, 2, dims, strides, box);
+    strides[1] = nb1 > 1 ? (uint64_t)a->w_bs1 * 2 : strides[0] * dims[1];
+    strides[2] = nb0 > 1 ? (uint64_t)a->w_bs0 * 2 : strides[1] * dims[2];
+    int rc = make_tmap_f16(&tmW, a->w, 4, dims, strides, box);
     if (rc) return rc;
     if (!a->x_mn_major) {
       dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)a->T; box[0] = BK; box[1] = (uint32_t)pl.BN;
@@ -371,7 +385,9 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
       dims[0] = (uint64_t)a->T; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
     }
     strides[0] = (uint64_t)a->ldx * 2;
-    rc = make_tmap_f16(&tmX, a->x, 2, dims, strides, box);
+    strides[1] = nb1 > 1 ? (uint64_t)a->x_bs1 * 2 : strides[0] * dims[1];
+    strides[2] = nb0 > 1 ? (uint64_t)a->x_bs0 * 2 : strides[1] * dims[2];
+    rc = make_tmap_f16(&tmX, a->x, 4, dims, strides, box);
     if (rc) return rc;
   }
 
@@ -383,12 +399,14 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   p.x_mn = a->x_mn_major; p.w_mn = a->w_mn_major;
   p.idesc = make_idesc_f16(BM, pl.BN, a->w_mn_major, a->x_mn_major);
   p.partial = reinterpret_cast<float*>(a->workspace);
+  p.nb1 = nb1; p.nbatch = nbatch; p.o_bs0 = a->o_bs0; p.o_bs1 = a->o_bs1;
   p.ep.bias = reinterpret_cast<const __half*>(a->bias);
   p.ep.act = a->act; p.ep.round_acc = a->round_acc;
   p.ep.scale_cols = a->scale_cols; p.ep.scale = a->scale;
   p.ep.res = a->res; p.ep.res_dtype = a->res_dtype; p.ep.ldr = a->ldr;
   p.ep.out = a->out; p.ep.out_dtype = a->out_dtype; p.ep.ldo = a->ldo;
   p.ep.group_rows = a->out_group_rows; p.ep.group_stride = a->out_group_stride;
+  p.ep.alpha = a->alpha_set ? a->alpha : 1.0f;
 
   const size_t smem_bytes = (size_t)pl.num_stages * pl.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
@@ -396,7 +414,7 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
     MYR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int units = pl.n_tt * pl.n_ft * pl.ksplit;
+  const int units = pl.n_tt * pl.n_ft * pl.ksplit * nbatch;
   const int grid = units < sm_count() ? units : sm_count();
   gemm_tc_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmW, tmX, p);
   MYR_CHECK_LAUNCH();

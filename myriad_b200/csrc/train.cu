@@ -1,0 +1,552 @@
+// Backward-pass row / elementwise kernels (HBM-bound, coalesced, 16-byte vectorised where the layout allows):
+// clamp-CE loss fwd+bwd, LayerNorm/RMSNorm backward, SwiGLU / GELU backward, RoPE backward, masked row softmax and
+// its backward (attention backward = batched tcgen05 GEMMs around these), row gather/scatter, LoraAdaptorV2 wgrad,
+// column sums (bias / base_prompts grads), fused AdamW over the flat parameter buffer.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace myr {
+
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block reductions for 256-thread blocks; result broadcast to all threads
+__device__ __forceinline__ float block_sum_t(float v, float* red) {
+  v = warp_sum_t(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+__device__ __forceinline__ float block_max_t(float v, float* red) {
+  v = warp_max_t(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, red[w]);
+  return t;
+}
+
+static inline int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// clamp_CE_loss (modeling_llama.py:718-728): softmax -> clamp[1e-7, 1-1e-7] -> log -> NLL(mean over labels != -100)
+// fwd: one CTA per row; stats[row] = (max, sumexp); row_loss[row] = -log(clamp(p_y)) or 0 when ignored
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ logits, long long ld, int V,
+                                                     const long long* __restrict__ labels, float* __restrict__ row_loss,
+                                                     float* __restrict__ stats) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const float* row = logits + (size_t)r * ld;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, row[i]);
+  m = block_max_t(m, red);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(row[i] - m);
+  s = block_sum_t(s, red);
+  if (threadIdx.x == 0) {
+    stats[2 * r] = m;
+    stats[2 * r + 1] = s;
+    const long long y = labels[r];
+    float l = 0.f;
+    if (y >= 0) {
+      float p = expf(row[y] - m) / s;
+      p = fminf(fmaxf(p, 1e-7f), 1.f - 1e-7f);
+      l = -logf(p);
+    }
+    row_loss[r] = l;
+  }
+}
+
+// loss_out[0] = mean loss, loss_out[1] = number of supervised rows (fixed summation order: deterministic)
+__global__ void __launch_bounds__(256) ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict__ labels,
+                                                        int R, float* __restrict__ loss_out) {
+  __shared__ float red[8];
+  float s = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < R; i += blockDim.x) {
+    if (labels[i] >= 0) {
+      s += row_loss[i];
+      c += 1.f;
+    }
+  }
+  s = block_sum_t(s, red);
+  c = block_sum_t(c, red);
+  if (threadIdx.x == 0) {
+    loss_out[0] = c > 0.f ? s / c : 0.f;
+    loss_out[1] = c;
+  }
+}
+
+// dlogits[r, j] = loss_scale / count * (p_j - [j == y]) if the row is supervised and p_y is strictly inside the clamp
+// interval (the clamp has zero gradient outside), else 0. fp16 output (GEMM operand of the lm_head dgrad).
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ logits, long long ld, int V,
+                                                     const long long* __restrict__ labels, const float* __restrict__ stats,
+                                                     const float* __restrict__ loss_out, float loss_scale,
+                                                     __half* __restrict__ dlogits, long long ldd) {
+  const int r = blockIdx.x;
+  const float* row = logits + (size_t)r * ld;
+  __half* drow = dlogits + (size_t)r * ldd;
+  const long long y = labels[r];
+  const float m = stats[2 * r], s = stats[2 * r + 1];
+  float g = 0.f;
+  if (y >= 0) {
+    const float py = expf(row[y] - m) / s;
+    if (py > 1e-7f && py < 1.f - 1e-7f) g = loss_scale / loss_out[1];
+  }
+  const float inv = 1.f / s;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    float d = 0.f;
+    if (g != 0.f) d = g * (expf(row[i] - m) * inv - (i == y ? 1.f : 0.f));
+    drow[i] = __float2half_rn(d);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm backward w.r.t. the input (gamma/beta are frozen on this path):
+//   xhat = (x - mean) * rstd;  gy = gamma * dy;  dx = rstd * (gy - mean(gy) - xhat * mean(gy * xhat))   (LN)
+//                                                dx = rstd * (gy - xhat * mean(gy * xhat))               (RMS, mean = 0)
+// x fp32 pre-norm rows (statistics recomputed), dy fp16 or fp32, optional `add` (fp32 residual-branch gradient)
+// out32 = dx + add. One CTA per row, D <= 4096.
+// ---------------------------------------------------------------------------------------------------
+struct NormBwdParams {
+  const float* x; long long ldx;
+  const void* dy; int dy_dtype; long long lddy;
+  const float* gamma; float eps; int rms; int D;
+  const float* add; long long ldadd;
+  float* out32; long long ldo;
+  __half* out16; long long ldo16;
+};
+
+__global__ void __launch_bounds__(256) norm_bwd_kernel(const NormBwdParams p) {
+  __shared__ float red[8];
+  const int row = blockIdx.x;
+  const float* x = p.x + (size_t)row * p.ldx;
+  constexpr int MAXI = 16;
+  float xv[MAXI], gv[MAXI];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = threadIdx.x + i * 256;
+    xv[i] = c < p.D ? x[c] : 0.f;
+    s += xv[i];
+  }
+  float mean = 0.f;
+  if (!p.rms) mean = block_sum_t(s, red) / p.D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < p.D) q += (xv[i] - mean) * (xv[i] - mean);
+  }
+  const float rstd = rsqrtf(block_sum_t(q, red) / p.D + p.eps);
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = threadIdx.x + i * 256;
+    gv[i] = 0.f;
+    if (c < p.D) {
+      const float dy = p.dy_dtype == MYR_F32 ? reinterpret_cast<const float*>(p.dy)[(size_t)row * p.lddy + c]
+                                             : __half2float(reinterpret_cast<const __half*>(p.dy)[(size_t)row * p.lddy + c]);
+      gv[i] = dy * p.gamma[c];
+      xv[i] = (xv[i] - mean) * rstd;
+      a += gv[i];
+      b += gv[i] * xv[i];
+    }
+  }
+  a = p.rms ? 0.f : block_sum_t(a, red) / p.D;
+  b = block_sum_t(b, red) / p.D;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < p.D) {
+      float dx = rstd * (gv[i] - a - xv[i] * b);
+      if (p.add) dx += p.add[(size_t)row * p.ldadd + c];
+      if (p.out32) p.out32[(size_t)row * p.ldo + c] = dx;
+      if (p.out16) p.out16[(size_t)row * p.ldo16 + c] = __float2half_rn(dx);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// activation backward
+// ---------------------------------------------------------------------------------------------------
+// SwiGLU: dgu[:, :I] = dact * u * (sig + g * sig * (1 - sig)); dgu[:, I:] = dact * silu(g)
+__global__ void swiglu_bwd_kernel(const __half* __restrict__ gu, long long ldg, const __half* __restrict__ dact, long long lda,
+                                  __half* __restrict__ dgu, long long ldd, int T, int I) {
+  const long long total = (long long)T * I;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / I;
+    const int c = (int)(i % I);
+    const float g = __half2float(gu[t * ldg + c]), u = __half2float(gu[t * ldg + I + c]), d = __half2float(dact[t * lda + c]);
+    const float sig = 1.f / (1.f + expf(-g));
+    dgu[t * ldd + c] = __float2half_rn(d * u * (sig + g * sig * (1.f - sig)));
+    dgu[t * ldd + I + c] = __float2half_rn(d * g * sig);
+  }
+}
+
+// GELU(erf) fwd from a saved pre-activation, and its backward: dpre = dy * (Phi(x) + x * phi(x))
+__global__ void gelu_fwd_kernel(const __half* __restrict__ pre, __half* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(gelu_erf(__half2float(pre[i])));
+}
+__global__ void gelu_bwd_kernel(const __half* __restrict__ pre, const __half* __restrict__ dy, __half* __restrict__ dpre,
+                                long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = __half2float(pre[i]);
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+    dpre[i] = __float2half_rn(__half2float(dy[i]) * (cdf + x * pdf));
+  }
+}
+
+// RoPE backward on the q and k thirds of dqkv rows (inverse rotation), in place.
+__global__ void rope_bwd_kernel(__half* __restrict__ dqkv, long long ld, int T, int H, int dh, const int* __restrict__ pos,
+                                const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+  const int half = dh >> 1;
+  const long long total = (long long)T * 2 * H * half;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % half);
+    long long r = i / half;
+    const int h = (int)(r % H);
+    r /= H;
+    const int which = (int)(r % 2);
+    const long long t = r / 2;
+    const float c = cos_t[(size_t)pos[t] * half + j], s = sin_t[(size_t)pos[t] * half + j];
+    __half* p = dqkv + t * ld + (size_t)which * H * dh + h * dh;
+    const float d1 = __half2float(p[j]), d2 = __half2float(p[half + j]);
+    p[j] = __float2half_rn(d1 * c + d2 * s);
+    p[half + j] = __float2half_rn(d2 * c - d1 * s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// attention backward helpers on materialised score rows [n_rows = B*H*Sq, ld] (Sq, Skv <= a few hundred)
+//   softmax: P = softmax(scale * S + mask) fp16; key j visible iff j < kv_len[b] && (!causal || j <= i); pad cols -> 0
+//   bwd    : dS = scale * P * (dP - sum_j dP * P) fp16
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long lds, __half* __restrict__ P,
+                                                           long long ldp, int H, int Sq, int Skv, int cols, float scale,
+                                                           int causal, const int* __restrict__ kv_len) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const int i = (int)(row % Sq);
+  const int b = (int)(row / ((long long)Sq * H));
+  const int kvl = kv_len ? min(kv_len[b], Skv) : Skv;
+  const int lim = causal ? min(kvl, i + 1) : kvl;
+  const float* s = S + row * lds;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < lim; j += blockDim.x) m = fmaxf(m, s[j] * scale);
+  m = block_max_t(m, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < lim; j += blockDim.x) sum += expf(s[j] * scale - m);
+  sum = block_sum_t(sum, red);
+  const float inv = sum > 0.f ? 1.f / sum : 0.f;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x)
+    P[row * ldp + j] = __float2half_rn(j < lim ? expf(s[j] * scale - m) * inv : 0.f);
+}
+
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const __half* __restrict__ P, long long ldp,
+                                                               const float* __restrict__ dP, long long lddp,
+                                                               __half* __restrict__ dS, long long lds, int cols, float scale) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float p = __half2float(P[row * ldp + j]);
+    if (p != 0.f) acc += p * dP[row * lddp + j];  // masked / padded columns of dP may hold uninitialised values
+  }
+  acc = block_sum_t(acc, red);
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float p = __half2float(P[row * ldp + j]);
+    dS[row * lds + j] = __float2half_rn(p != 0.f ? scale * p * (dP[row * lddp + j] - acc) : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row gather / scatter with cast:  dst[r, :] = src[idx[r], :]   or   dst[idx[r], :] = src[r, :]
+// ---------------------------------------------------------------------------------------------------
+__global__ void index_rows_kernel(const void* __restrict__ src, int src_dtype, long long src_ld, void* __restrict__ dst,
+                                  int dst_dtype, long long dst_ld, const int* __restrict__ idx, int R, int D, int scatter) {
+  const long long total = (long long)R * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D;
+    const int c = (int)(i % D);
+    const long long sr = scatter ? r : idx[r], dr = scatter ? idx[r] : r;
+    const float v = src_dtype == MYR_F32 ? reinterpret_cast<const float*>(src)[sr * src_ld + c]
+                                         : __half2float(reinterpret_cast<const __half*>(src)[sr * src_ld + c]);
+    if (dst_dtype == MYR_F32)
+      reinterpret_cast<float*>(dst)[dr * dst_ld + c] = v;
+    else
+      reinterpret_cast<__half*>(dst)[dr * dst_ld + c] = __float2half_rn(v);
+  }
+}
+
+// column sums over grouped rows: out[c] (+)= scale * sum_{g < groups, r < rows} src[g * gs + r * ld + c]
+// (bias gradients; base_prompts gradient with rows = 1 per prompt). Deterministic: one thread per column.
+__global__ void colsum_kernel(const void* __restrict__ src, int src_dtype, long long ld, long long gs, int groups, int rows,
+                              int D, float scale, float* __restrict__ out, int accumulate) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < D; c += gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int g = 0; g < groups; ++g)
+      for (int r = 0; r < rows; ++r) {
+        const long long o = g * gs + r * ld + c;
+        a += src_dtype == MYR_F32 ? reinterpret_cast<const float*>(src)[o] : __half2float(reinterpret_cast<const __half*>(src)[o]);
+      }
+    out[c] = (accumulate ? out[c] : 0.f) + scale * a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LoraAdaptorV2 backward (networks.py:81-93, y = x + W2 (W1 x)): weights only (x comes from the frozen ViT).
+//   pass 1 (one warp per row): t = W1 x, dt = W2^T dy          -> td [rows, 2 * rank]
+//   pass 2 (one thread per column i): dW2[i, r] = sum_rows dy[row, i] t[row, r]; dW1[r, i] = sum_rows dt[row, r] x[row, i]
+// ---------------------------------------------------------------------------------------------------
+__global__ void adaptor_bwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ w1,
+                                        const float* __restrict__ w2, float* __restrict__ td, int rows, int D, int rank) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float t[4] = {0.f, 0.f, 0.f, 0.f}, dt[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = lane; i < D; i += 32) {
+    const float xv = x[(size_t)warp * D + i], dv = dy[(size_t)warp * D + i];
+    for (int r = 0; r < rank; ++r) {
+      t[r] += xv * w1[(size_t)r * D + i];
+      dt[r] += dv * w2[(size_t)i * rank + r];
+    }
+  }
+  for (int r = 0; r < rank; ++r) {
+    t[r] = warp_sum_t(t[r]);
+    dt[r] = warp_sum_t(dt[r]);
+  }
+  if (lane == 0)
+    for (int r = 0; r < rank; ++r) {
+      td[(size_t)warp * 2 * rank + r] = t[r];
+      td[(size_t)warp * 2 * rank + rank + r] = dt[r];
+    }
+}
+__global__ void adaptor_bwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ td,
+                                        float* __restrict__ dw1, float* __restrict__ dw2, int rows, int D, int rank, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int row = 0; row < rows; ++row) {
+    const float xv = x[(size_t)row * D + i], dv = dy[(size_t)row * D + i];
+    for (int r = 0; r < rank; ++r) {
+      a2[r] += dv * td[(size_t)row * 2 * rank + r];
+      a1[r] += td[(size_t)row * 2 * rank + rank + r] * xv;
+    }
+  }
+  for (int r = 0; r < rank; ++r) {
+    dw2[(size_t)i * rank + r] = scale * a2[r];
+    dw1[(size_t)r * D + i] = scale * a1[r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused AdamW over the flat fp32 parameter / gradient / moment buffers (runner_base.py:105-139 semantics:
+// weight decay only where wd_mask != 0), with gradient unscaling (GradScaler.unscale_) folded in.
+// found_inf (device int) != 0 skips the update (GradScaler.step).
+// ---------------------------------------------------------------------------------------------------
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             const unsigned char* __restrict__ wd_mask, long long n, float lr, float beta1, float beta2,
+                             float eps, float wd, float bc1, float bc2, float inv_scale, const int* __restrict__ found_inf) {
+  if (found_inf && *found_inf) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gr = g[i] * inv_scale;
+    float pv = p[i];
+    if (wd_mask[i]) pv *= 1.f - lr * wd;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gr;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gr * gr;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pv - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  }
+}
+__global__ void check_finite_kernel(const float* __restrict__ g, long long n, int* __restrict__ found_inf) {
+  int bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!isfinite(g[i])) bad = 1;
+  if (bad) atomicExch(found_inf, 1);
+}
+
+}  // namespace myr
+
+using namespace myr;
+
+#define STREAM cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_)
+
+extern "C" int myr_clamp_ce_fwd(const void* logits, int64_t ld, int32_t R, int32_t V, const void* labels, void* row_loss,
+                                void* stats, void* loss_out, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(logits && labels && row_loss && stats && loss_out && R > 0 && V > 0, "clamp_ce_fwd: bad arguments");
+  ce_fwd_kernel<<<R, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), ld, V, reinterpret_cast<const long long*>(labels),
+                                       reinterpret_cast<float*>(row_loss), reinterpret_cast<float*>(stats));
+  MYR_CHECK_LAUNCH();
+  ce_reduce_kernel<<<1, 256, 0, stream>>>(reinterpret_cast<const float*>(row_loss), reinterpret_cast<const long long*>(labels), R,
+                                          reinterpret_cast<float*>(loss_out));
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_clamp_ce_bwd(const void* logits, int64_t ld, int32_t R, int32_t V, const void* labels, const void* stats,
+                                const void* loss_out, float loss_scale, void* dlogits, int64_t ldd, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(logits && labels && stats && loss_out && dlogits && R > 0 && V > 0, "clamp_ce_bwd: bad arguments");
+  ce_bwd_kernel<<<R, 256, 0, stream>>>(reinterpret_cast<const float*>(logits), ld, V, reinterpret_cast<const long long*>(labels),
+                                       reinterpret_cast<const float*>(stats), reinterpret_cast<const float*>(loss_out), loss_scale,
+                                       reinterpret_cast<__half*>(dlogits), ldd);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_norm_bwd(const void* x, int64_t ldx, const void* dy, int32_t dy_dtype, int64_t lddy, const void* gamma,
+                            float eps, int32_t rms, int32_t rows, int32_t D, const void* add, int64_t ldadd, void* out32,
+                            int64_t ldo, void* out16, int64_t ldo16, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(x && dy && gamma && rows > 0 && D > 0 && D <= 4096 && (out32 || out16), "norm_bwd: bad arguments (D <= 4096)");
+  NormBwdParams p;
+  p.x = reinterpret_cast<const float*>(x); p.ldx = ldx; p.dy = dy; p.dy_dtype = dy_dtype; p.lddy = lddy;
+  p.gamma = reinterpret_cast<const float*>(gamma); p.eps = eps; p.rms = rms; p.D = D;
+  p.add = reinterpret_cast<const float*>(add); p.ldadd = ldadd;
+  p.out32 = reinterpret_cast<float*>(out32); p.ldo = ldo; p.out16 = reinterpret_cast<__half*>(out16); p.ldo16 = ldo16;
+  norm_bwd_kernel<<<rows, 256, 0, stream>>>(p);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_swiglu_bwd(const void* gate_up, int64_t ld_gu, const void* dact, int64_t ld_da, void* dgu, int64_t ld_dgu,
+                              int32_t T, int32_t I, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(gate_up && dact && dgu && T > 0 && I > 0, "swiglu_bwd: bad arguments");
+  swiglu_bwd_kernel<<<grid_for((long long)T * I, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(gate_up), ld_gu,
+                                                                        reinterpret_cast<const __half*>(dact), ld_da,
+                                                                        reinterpret_cast<__half*>(dgu), ld_dgu, T, I);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_gelu_fwd(const void* pre, void* out, int64_t n, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(pre && out && n > 0, "gelu_fwd: bad arguments");
+  gelu_fwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(pre), reinterpret_cast<__half*>(out), n);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(pre && dy && dpre && n > 0, "gelu_bwd: bad arguments");
+  gelu_bwd_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(pre), reinterpret_cast<const __half*>(dy),
+                                                        reinterpret_cast<__half*>(dpre), n);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_rope_bwd(void* dqkv, int64_t ld, int32_t T, int32_t H, int32_t dh, const void* pos, const void* cos_table,
+                            const void* sin_table, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(dqkv && pos && cos_table && sin_table && T > 0 && dh % 2 == 0, "rope_bwd: bad arguments");
+  rope_bwd_kernel<<<grid_for((long long)T * 2 * H * (dh / 2), 256), 256, 0, stream>>>(
+      reinterpret_cast<__half*>(dqkv), ld, T, H, dh, reinterpret_cast<const int*>(pos), reinterpret_cast<const float*>(cos_table),
+      reinterpret_cast<const float*>(sin_table));
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_softmax_rows(const void* S, int64_t lds, void* P, int64_t ldp, int32_t B, int32_t H, int32_t Sq, int32_t Skv,
+                                int32_t cols, float scale, int32_t causal, const void* kv_len, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(S && P && B > 0 && H > 0 && Sq > 0 && Skv > 0 && cols >= Skv, "softmax_rows: bad arguments");
+  softmax_rows_kernel<<<B * H * Sq, 256, 0, stream>>>(reinterpret_cast<const float*>(S), lds, reinterpret_cast<__half*>(P), ldp, H,
+                                                      Sq, Skv, cols, scale, causal, reinterpret_cast<const int*>(kv_len));
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_softmax_bwd_rows(const void* P, int64_t ldp, const void* dP, int64_t lddp, void* dS, int64_t lds,
+                                    int64_t n_rows, int32_t cols, float scale, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(P && dP && dS && n_rows > 0 && cols > 0, "softmax_bwd_rows: bad arguments");
+  softmax_bwd_rows_kernel<<<(unsigned)n_rows, 256, 0, stream>>>(reinterpret_cast<const __half*>(P), ldp,
+                                                               reinterpret_cast<const float*>(dP), lddp,
+                                                               reinterpret_cast<__half*>(dS), lds, cols, scale);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_index_rows(const void* src, int32_t src_dtype, int64_t src_ld, void* dst, int32_t dst_dtype, int64_t dst_ld,
+                              const void* idx, int32_t R, int32_t D, int32_t scatter, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(src && dst && idx && R > 0 && D > 0, "index_rows: bad arguments");
+  index_rows_kernel<<<grid_for((long long)R * D, 256), 256, 0, stream>>>(src, src_dtype, src_ld, dst, dst_dtype, dst_ld,
+                                                                        reinterpret_cast<const int*>(idx), R, D, scatter);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_t group_stride, int32_t groups, int32_t rows,
+                          int32_t D, float scale, void* out, int32_t accumulate, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(src && out && groups > 0 && rows > 0 && D > 0, "colsum: bad arguments");
+  colsum_kernel<<<ceil_div(D, 128), 128, 0, stream>>>(src, src_dtype, ld, group_stride, groups, rows, D, scale,
+                                                     reinterpret_cast<float*>(out), accumulate);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_adaptor_bwd(const void* x, const void* dy, const void* w1, const void* w2, void* scratch, void* dw1,
+                               void* dw2, int32_t rows, int32_t D, int32_t rank, float scale, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(x && dy && w1 && w2 && scratch && dw1 && dw2 && rows > 0 && D > 0 && rank > 0 && rank <= 4, "adaptor_bwd: bad arguments");
+  adaptor_bwd_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(
+      reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(w1),
+      reinterpret_cast<const float*>(w2), reinterpret_cast<float*>(scratch), rows, D, rank);
+  MYR_CHECK_LAUNCH();
+  adaptor_bwd_cols_kernel<<<ceil_div(D, 128), 128, 0, stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(dy),
+                                                               reinterpret_cast<const float*>(scratch), reinterpret_cast<float*>(dw1),
+                                                               reinterpret_cast<float*>(dw2), rows, D, rank, scale);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_adamw_step(void* params, const void* grads, void* exp_avg, void* exp_avg_sq, const void* wd_mask, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float inv_scale,
+                              void* found_inf, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && wd_mask && n > 0 && step > 0, "adamw_step: bad arguments");
+  if (found_inf) {
+    MYR_CHECK_CUDA(cudaMemsetAsync(found_inf, 0, sizeof(int), stream));
+    check_finite_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(grads), n, reinterpret_cast<int*>(found_inf));
+    MYR_CHECK_LAUNCH();
+  }
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adamw_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<float*>(params), reinterpret_cast<const float*>(grads),
+                                                     reinterpret_cast<float*>(exp_avg), reinterpret_cast<float*>(exp_avg_sq),
+                                                     reinterpret_cast<const unsigned char*>(wd_mask), n, lr, beta1, beta2, eps,
+                                                     weight_decay, bc1, bc2, inv_scale, reinterpret_cast<const int*>(found_inf));
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_memset_zero(void* ptr, size_t bytes, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(ptr != nullptr, "memset_zero: null pointer");
+  MYR_CHECK_CUDA(cudaMemsetAsync(ptr, 0, bytes, stream));
+  return MYR_OK;
+}

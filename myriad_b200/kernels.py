@@ -42,6 +42,10 @@ class GemmArgs(ctypes.Structure):
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("bn_hint", ctypes.c_int32), ("ksplit_hint", ctypes.c_int32),
         ("out_group_rows", ctypes.c_int32), ("out_group_stride", ctypes.c_int64),
+        ("nb0", ctypes.c_int32), ("nb1", ctypes.c_int32),
+        ("x_bs0", ctypes.c_int64), ("x_bs1", ctypes.c_int64), ("w_bs0", ctypes.c_int64), ("w_bs1", ctypes.c_int64),
+        ("o_bs0", ctypes.c_int64), ("o_bs1", ctypes.c_int64),
+        ("alpha_set", ctypes.c_int32), ("alpha", ctypes.c_float),
     ]
 
 
@@ -60,10 +64,12 @@ def workspace(nbytes, device):
 
 def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.float16, scale_cols=0, scale=1.0,
          round_acc=False, x_mn_major=False, w_mn_major=False, T=None, F=None, K=None, bn_hint=0, ksplit_hint=0,
-         out_group_rows=0, out_group_stride=0, ldo=None):
+         out_group_rows=0, out_group_stride=0, ldo=None, ldx=None, ldw=None, batch=None, alpha=None):
+    # batch = (nb0, nb1, (x_bs0, x_bs1), (w_bs0, w_bs1), (o_bs0, o_bs1)): independent problems, element strides
     """out[t, f] = epilogue(sum_k x[t, k] * w[f, k]);  x: [T, K] fp16 (row stride may exceed K), w: [F, K] fp16."""
     assert x.dtype == torch.float16 and w.dtype == torch.float16
     assert x.stride(-1) == 1 and w.stride(-1) == 1
+    assert batch is None or (T is not None and F is not None and K is not None and out is not None and ldo is not None)
     if T is None:
         T = x.shape[0] if not x_mn_major else x.shape[1]
     if K is None:
@@ -74,8 +80,11 @@ def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.floa
         out = torch.empty((T, F), dtype=out_dtype, device=x.device)
     ws = workspace(64 << 20, x.device)
     a = GemmArgs()
-    a.x, a.ldx = x.data_ptr(), x.stride(0)
-    a.w, a.ldw = w.data_ptr(), w.stride(0)
+    a.x, a.ldx = x.data_ptr(), (ldx if ldx is not None else x.stride(0))
+    a.w, a.ldw = w.data_ptr(), (ldw if ldw is not None else w.stride(0))
+    if batch is not None:
+        a.nb0, a.nb1 = batch[0], batch[1]
+        (a.x_bs0, a.x_bs1), (a.w_bs0, a.w_bs1), (a.o_bs0, a.o_bs1) = batch[2], batch[3], batch[4]
     a.T, a.F, a.K = T, F, K
     a.x_mn_major, a.w_mn_major = int(x_mn_major), int(w_mn_major)
     a.bias = bias.data_ptr() if bias is not None else None
@@ -95,6 +104,8 @@ def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.floa
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     a.bn_hint, a.ksplit_hint = bn_hint, ksplit_hint
     a.out_group_rows, a.out_group_stride = out_group_rows, out_group_stride
+    if alpha is not None:
+        a.alpha_set, a.alpha = 1, alpha
     check(lib().myr_gemm_f16(ctypes.byref(a), _stream()), "myr_gemm_f16")
     return out
 
@@ -251,3 +262,102 @@ def launch_count():
 def note_graph_replay(n_nodes):
     global _graph_replay_launches
     _graph_replay_launches += n_nodes
+
+
+# ----------------------------------------------------------------------------------------------- training kernels
+def _f32(v):
+    return ctypes.c_float(v)
+
+
+def clamp_ce_fwd(logits, labels, row_loss, stats, loss_out):
+    R, V = logits.shape
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64
+    check(lib().myr_clamp_ce_fwd(_p(logits), _i64(logits.stride(0)), R, V, _p(labels), _p(row_loss), _p(stats), _p(loss_out), _stream()),
+          "myr_clamp_ce_fwd")
+
+
+def clamp_ce_bwd(logits, labels, stats, loss_out, loss_scale, dlogits):
+    R, V = logits.shape
+    check(lib().myr_clamp_ce_bwd(_p(logits), _i64(logits.stride(0)), R, V, _p(labels), _p(stats), _p(loss_out), _f32(loss_scale),
+                                 _p(dlogits), _i64(dlogits.stride(0)), _stream()), "myr_clamp_ce_bwd")
+
+
+def norm_bwd(x, dy, gamma, eps, rms=False, add=None, out32=None, out16=None):
+    rows, D = x.shape
+    assert x.dtype == torch.float32
+    check(lib().myr_norm_bwd(_p(x), _i64(x.stride(0)), _p(dy), _dt(dy), _i64(dy.stride(0)), _p(gamma), _f32(eps), int(rms), rows, D,
+                             _p(add), _i64(add.stride(0) if add is not None else 0), _p(out32),
+                             _i64(out32.stride(0) if out32 is not None else 0), _p(out16),
+                             _i64(out16.stride(0) if out16 is not None else 0), _stream()), "myr_norm_bwd")
+
+
+def swiglu_bwd(gu, dact, dgu, T, I):
+    check(lib().myr_swiglu_bwd(_p(gu), _i64(gu.stride(0)), _p(dact), _i64(dact.stride(0)), _p(dgu), _i64(dgu.stride(0)), T, I, _stream()),
+          "myr_swiglu_bwd")
+
+
+def gelu_fwd(pre, out):
+    check(lib().myr_gelu_fwd(_p(pre), _p(out), _i64(pre.numel()), _stream()), "myr_gelu_fwd")
+
+
+def gelu_bwd(pre, dy, dpre):
+    check(lib().myr_gelu_bwd(_p(pre), _p(dy), _p(dpre), _i64(pre.numel()), _stream()), "myr_gelu_bwd")
+
+
+def rope_bwd(dqkv, T, H, dh, pos, cos, sin):
+    check(lib().myr_rope_bwd(_p(dqkv), _i64(dqkv.stride(0)), T, H, dh, _p(pos), _p(cos), _p(sin), _stream()), "myr_rope_bwd")
+
+
+def softmax_rows(S, P, B, H, Sq, Skv, cols, scale, causal=False, kv_len=None):
+    check(lib().myr_softmax_rows(_p(S), _i64(cols), _p(P), _i64(cols), B, H, Sq, Skv, cols, _f32(scale), int(causal), _p(kv_len),
+                                 _stream()), "myr_softmax_rows")
+
+
+def softmax_bwd_rows(P, dP, dS, n_rows, cols, scale):
+    check(lib().myr_softmax_bwd_rows(_p(P), _i64(cols), _p(dP), _i64(cols), _p(dS), _i64(cols), _i64(n_rows), cols, _f32(scale),
+                                     _stream()), "myr_softmax_bwd_rows")
+
+
+def index_rows(src, dst, idx, D, scatter=False):
+    assert idx.dtype == torch.int32
+    check(lib().myr_index_rows(_p(src), _dt(src), _i64(src.stride(0)), _p(dst), _dt(dst), _i64(dst.stride(0)), _p(idx), idx.numel(), D,
+                               int(scatter), _stream()), "myr_index_rows")
+
+
+def colsum(src, ld, group_stride, groups, rows, D, out, scale=1.0, accumulate=False):
+    check(lib().myr_colsum(_p(src), _dt(src), _i64(ld), _i64(group_stride), groups, rows, D, _f32(scale), _p(out), int(accumulate),
+                           _stream()), "myr_colsum")
+
+
+def adaptor_bwd(x, dy, w1, w2, scratch, dw1, dw2, rows, D, rank, scale):
+    check(lib().myr_adaptor_bwd(_p(x), _p(dy), _p(w1), _p(w2), _p(scratch), _p(dw1), _p(dw2), rows, D, rank, _f32(scale), _stream()),
+          "myr_adaptor_bwd")
+
+
+def adamw_step(params, grads, m, v, wd_mask, lr, beta1, beta2, eps, wd, step, inv_scale=1.0, found_inf=None):
+    check(lib().myr_adamw_step(_p(params), _p(grads), _p(m), _p(v), _p(wd_mask), _i64(params.numel()), _f32(lr), _f32(beta1),
+                               _f32(beta2), _f32(eps), _f32(wd), step, _f32(inv_scale), _p(found_inf), _stream()), "myr_adamw_step")
+
+
+def memset_zero(t):
+    check(lib().myr_memset_zero(_p(t), ctypes.c_size_t(t.numel() * t.element_size()), _stream()), "myr_memset_zero")
+
+
+def conv3x3_relu(x, w, bias, out, B, H, W, Cin, Cout):
+    check(lib().myr_conv3x3_relu(_p(x), _dt(x), _p(w), _p(bias), _p(out), B, H, W, Cin, Cout, _stream()), "myr_conv3x3_relu")
+
+
+def pool_relu_bwd(y, dpool, dy, B, H, W, C):
+    check(lib().myr_pool_relu_bwd(_p(y), _p(dpool), _dt(dpool), _p(dy), B, H, W, C, _stream()), "myr_pool_relu_bwd")
+
+
+def conv3x3_wgrad(x, dy, dw, db, B, H, W, Cin, Cout, scale):
+    check(lib().myr_conv3x3_wgrad(_p(x), _dt(x), _p(dy), _p(dw), _p(db), B, H, W, Cin, Cout, _f32(scale), _stream()), "myr_conv3x3_wgrad")
+
+
+def conv3x3_dgrad(dy, w, din, B, H, W, Cin, Cout):
+    check(lib().myr_conv3x3_dgrad(_p(dy), _p(w), _p(din), B, H, W, Cin, Cout, _stream()), "myr_conv3x3_dgrad")
+
+
+def col2im(dcols, din, B, H, W, C, KH, KW, pad):
+    check(lib().myr_col2im(_p(dcols), _p(din), B, H, W, C, KH, KW, pad, _stream()), "myr_col2im")
