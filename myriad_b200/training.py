@@ -149,7 +149,7 @@ class MyriadTrainer(MyriadEngine):
     def _refresh_late(self):
         self.vitw.ad1 = self.param("expert_adaptor.conv1.weight")
         self.vitw.ad2 = self.param("expert_adaptor.conv2.weight")
-        if self.d.lora_r:
+        if self.d.lora_r and hasattr(self, "llw"):
             r, D = self.d.lora_r, self.d.llama.hidden
             for i, L in enumerate(self.llw.layers):
                 p = "llama_model.base_model.model.model.layers.%d.self_attn." % i
@@ -187,18 +187,15 @@ class MyriadTrainer(MyriadEngine):
         return out
 
     # ------------------------------------------------------------------------------------ LoRA (trainer form)
-    def _llama_layer(self, L, li, h32, bufs, B, S, pos, kv_len, cache_off, cache_off_dev, Skv, causal, save=None):
-        """Same launch sequence as MyriadEngine._llama_layer with B unscaled + epilogue alpha; optionally keeps the
-        activations the backward needs (buffers are per-layer when `save` is given)."""
+    def _llama_layer(self, L, li, h32, bufs, B, S, pos, kv_len, cache_off, cache_off_dev, Skv, causal):
+        """Inference launch sequence of MyriadEngine._llama_layer, with the trainer's unscaled LoRA B (alpha / r applied in
+        the GEMM epilogue) so evaluation between optimizer steps uses the live parameters."""
         l = self.d.llama
         D, H, dh, T = l.hidden, l.heads, l.head_dim, B * S
         x16, qkv, ctx, gu, act = bufs
         kc, vc = self.kcache[li], self.vcache[li]
-        if save is not None:
-            save.h_in = h32.clone() if save.clone_h else h32
         K.norm(h32, L.n1, None, l.eps, rms=True, out16=x16)
         K.gemm(x16, L.wqkv, out=qkv)
-        xa = None
         if L.lora is not None:
             r = self.d.lora_r
             xa = K.gemm(x16, L.lora.a)
@@ -209,15 +206,26 @@ class MyriadTrainer(MyriadEngine):
         K.attention(qkv, kc, vc, ctx, B, H, S, Skv, dh, 1.0 / math.sqrt(dh), (3 * D, S * 3 * D, dh), cs, cs, (D, S * D, dh),
                     causal=causal, q_off=0, kv_len=kv_len)
         K.gemm(ctx, L.wo, res=h32, out=h32)
-        if save is not None:
-            save.h_mid = h32.clone()
-            save.x1, save.qkv, save.xa = x16, qkv, xa
-        K.norm(h32, L.n2, None, l.eps, rms=True, out16=x16 if save is None else ctx)  # ctx is free again: reuse as x2
-        K.gemm(x16 if save is None else ctx, L.wgu, out=gu)
+        K.norm(h32, L.n2, None, l.eps, rms=True, out16=x16)
+        K.gemm(x16, L.wgu, out=gu)
         K.swiglu(gu, act, T, l.inter)
         K.gemm(act, L.wd, res=h32, out=h32)
-        if save is not None:
-            save.gu = gu
+
+    # ------------------------------------------------------------------------------------------ small helpers
+    def _e(self, *shape, dtype=F16):
+        return torch.empty(*shape, device=self.dev, dtype=dtype)
+
+    def _cast16(self, src32, rows, D, src_ld=None, src_gs=0, groups=1):
+        """fp32 rows -> contiguous fp16 [groups * rows, D] (GEMM operand)."""
+        dst = self._e(groups * rows, D)
+        K.copy_rows(src32, dst, groups, rows, D, D if src_ld is None else src_ld, src_gs, D, rows * D)
+        return dst
+
+    def _norm_bwd(self, x, dy, gamma, eps, rms=False, add=None, want16=True):
+        out32 = self._e(*x.shape, dtype=F32)
+        out16 = self._e(*x.shape) if want16 else None
+        K.norm_bwd(x, dy, gamma, eps, rms=rms, add=add, out32=out32, out16=out16)
+        return out32, out16
 
     # --------------------------------------------------------------------------------------- attention backward
     def _attn_bwd(self, q, k, v, dctx, dq, dk, dv, B, H, Sq, Skv, dh, scale, causal, kv_len):
@@ -242,8 +250,8 @@ class MyriadTrainer(MyriadEngine):
         K.softmax_bwd_rows(P16, S32, dS16, n, Sp, scale)
         (dqt, dq_ts, dq_bs), (dkt, dk_ts, dk_bs), (dvt, dv_ts, dv_bs) = dq, dk, dv
         # dV[key, d] = sum_q P[q, key] dO[q, d]
-        K.gemm(P16, dctx, out=dvt.reshape(-1) if dvt.dim() == 1 else dvt, x_mn_major=True, w_mn_major=True, T=Skv, F=dh, K=Sq,
-               ldx=Sp, ldw=HD, ldo=dv_ts, bn_hint=64, batch=(B, H, obs, (Sq * HD, dh), (dv_bs, dh)))
+        K.gemm(P16, dctx, out=dvt, x_mn_major=True, w_mn_major=True, T=Skv, F=dh, K=Sq, ldx=Sp, ldw=HD, ldo=dv_ts, bn_hint=64,
+               batch=(B, H, obs, (Sq * HD, dh), (dv_bs, dh)))
         # dQ[q, d] = sum_key dS[q, key] K[key, d]
         K.gemm(dS16, kt, out=dqt, w_mn_major=True, T=Sq, F=dh, K=Skv, ldx=Sp, ldw=k_ts, ldo=dq_ts,
                batch=(B, H, obs, (k_bs, dh), (dq_bs, dh)))
@@ -274,9 +282,10 @@ class MyriadTrainer(MyriadEngine):
             x, Hc = xn, Hc // 2
         return x, saved
 
-    def _conv_trunk_bwd(self, dx, saved, W, inv_scale):
+    def _conv_trunk_bwd(self, dx, saved, W):
         """dx: fp16 gradient w.r.t. the trunk output [B,7,7,1024]; writes weight/bias grads into the flat buffer."""
         dev = self.dev
+        inv_scale = 1.0 / self.loss_scale
         B = dx.shape[0]
         for j in range(4, -1, -1):
             x, y, cols, Hc, cin, cout = saved[j]
@@ -298,3 +307,298 @@ class MyriadTrainer(MyriadEngine):
                 dcols = K.gemm(dy2, W.gemm[j - 3][0], w_mn_major=True, F=9 * cin, K=cout)
                 dx = torch.empty(B, Hc, Hc, cin, device=dev, dtype=F16)
                 K.col2im(dcols, dx, B, Hc, Hc, cin, 3, 3, 1)
+
+    def _ve_head_bwd(self, W, tp, d_tok16, B):
+        """Backward of the conv head (1x1 -> 768 for VEInstructor, 5x5 no-pad -> 4096 for VETokenizer) given the fp16
+        gradient of its token rows [B * n_tok, Cout]; continues into the trunk."""
+        inv_scale = 1.0 / self.loss_scale
+        gw, gb = self.grad("%s.meta_net.15.weight" % W.mod), self.grad("%s.meta_net.15.bias" % W.mod)
+        rows, cout = d_tok16.shape
+        kdim = W.head_k * W.head_k * 1024
+        K.gemm(d_tok16, tp.head_in, out=gw.reshape(cout, kdim), x_mn_major=True, w_mn_major=True, T=cout, F=kdim, K=rows, bn_hint=128,
+               alpha=inv_scale)
+        K.colsum(d_tok16, cout, 0, 1, rows, cout, gb, scale=inv_scale)
+        d_in = K.gemm(d_tok16, W.head_w, w_mn_major=True, F=kdim, K=cout)  # [rows, k*k*1024]
+        if W.head_k == 1:
+            dx = d_in.reshape(B, 7, 7, 1024)
+        else:
+            dx = self._e(B, 7, 7, 1024)
+            K.col2im(d_in, dx, B, 7, 7, 1024, W.head_k, W.head_k, 0)
+        self._conv_trunk_bwd(dx, tp.saved, W)
+
+    # ------------------------------------------------------------------------- encode_img with saved activations
+    def encode_img(self, image, maps, stage, out=None, out_batch_stride=None):
+        tp = getattr(self, "_tape", None)
+        if tp is None:
+            return super().encode_img(image, maps, stage, out, out_batch_stride)
+        d, dev = self.d, self.dev
+        B, N, Dv = image.shape[0], d.vit.tokens, d.vit.dim
+        Hq, Dl = d.qf.hidden, d.llama.hidden
+        W = self.vitw
+        tp.vit_x = self.vit_forward(image)  # frozen: forward only (nothing trainable below it)
+        enc16 = self._e(B * N, Dv)
+        tp.ad_pre = self._e(B * N, Dv, dtype=F32)
+        K.norm(tp.vit_x, W.ln_vision[0], W.ln_vision[1], 1e-5, out16=enc16, w1=W.ad1, w2=W.ad2, pre32=tp.ad_pre)
+        nq0 = d.qf.num_query
+        Q = nq0 + (49 if stage in (1, 2) else 0)
+        tp.B, tp.Q, tp.stage = B, Q, stage
+        q32 = self._e(B * Q, Hq, dtype=F32)
+        K.copy_rows(self.qfw.query_tokens, q32, B, nq0, Hq, Hq, 0, Hq, Q * Hq)
+        if stage in (1, 2):
+            tp.inst = _Obj()
+            trunk, tp.inst.saved = self._conv_trunk_train(maps, self.instw)
+            tp.inst.head_in = trunk.reshape(B * 49, 1024)
+            K.gemm(tp.inst.head_in, self.instw.head_w, bias=self.instw.head_b, out=q32[nq0:], out_group_rows=49,
+                   out_group_stride=Q * Hq, T=B * 49, ldo=Hq)
+        h16 = self._qformer_train(q32, enc16, B, Q, tp)
+        n_tok = self.num_image_tokens(stage)
+        if out is None:
+            out = torch.empty(B, n_tok, Dl, device=dev, dtype=F32)
+            out_batch_stride = n_tok * Dl
+        flat = out.reshape(-1)
+        K.gemm(h16, self.qfw.proj_w, bias=self.qfw.proj_b, out=flat, out_group_rows=Q, out_group_stride=out_batch_stride,
+               T=B * Q, ldo=Dl)
+        if stage in (0, 1):
+            Wt = self.tokw
+            tp.tok = _Obj()
+            trunk, tp.tok.saved = self._conv_trunk_train(maps, Wt)
+            tp.tok.head_in = self._e(B * 9, 25 * 1024)
+            K.im2col(trunk, tp.tok.head_in, B, 7, 7, 1024, 5, 5, 0)
+            K.copy_rows(Wt.base_prompts, flat[Q * Dl:], B, 9, Dl, Dl, 0, Dl, out_batch_stride)
+            K.gemm(tp.tok.head_in, Wt.head_w, bias=Wt.head_b, out=flat[(Q + 9) * Dl:], out_group_rows=9,
+                   out_group_stride=out_batch_stride, T=B * 9, ldo=Dl)
+        return out
+
+    def _qformer_train(self, q32, enc16, B, Q, tp):
+        """qformer_forward keeping what the input-gradient pass needs. Every Q-Former weight is frozen, so that is only:
+        pre-LayerNorm sums (fp32), q/k/v of both attentions, and the GELU pre-activation."""
+        q, W = self.d.qf, self.qfw
+        Hd, H = q.hidden, q.heads
+        dh = Hd // H
+        N = self.d.vit.tokens
+        T = B * Q
+        h32, h16 = self._e(T, Hd, dtype=F32), self._e(T, Hd)
+        ctx, ff = self._e(T, Hd), self._e(T, q.inter)
+        tp.q_in = q32
+        K.norm(q32, W.emb_ln[0], W.emb_ln[1], q.ln_eps, out16=h16, out32=h32)
+        tp.ckv = K.gemm(enc16, W.ckv_w, bias=W.ckv_b)
+        ldkv = tp.ckv.shape[1]
+        scale = 1.0 / math.sqrt(dh)
+        tp.qf = []
+        so = (Hd, Q * Hd, dh)
+        for L in W.layers:
+            S = _Obj()
+            S.qkv = K.gemm(h16, L.wqkv, bias=L.bqkv)
+            s = (3 * Hd, Q * 3 * Hd, dh)
+            K.attention(S.qkv, S.qkv[:, Hd:], S.qkv[:, 2 * Hd:], ctx, B, H, Q, Q, dh, scale, s, s, s, so)
+            S.tmp_a = K.gemm(ctx, L.wo, bias=L.bo, res=h32, out_dtype=F32)
+            K.norm(S.tmp_a, L.ln_a[0], L.ln_a[1], q.ln_eps, out16=h16, out32=h32)
+            if L.cross:
+                S.cq = K.gemm(h16, L.cq_w, bias=L.cq_b)
+                kk = tp.ckv[:, L.ckv_index * 2 * Hd:]
+                ks = (ldkv, N * ldkv, dh)
+                K.attention(S.cq, kk, kk[:, Hd:], ctx, B, H, Q, N, dh, scale, so, ks, ks, so)
+                S.tmp_c = K.gemm(ctx, L.co_w, bias=L.co_b, res=h32, out_dtype=F32)
+                K.norm(S.tmp_c, L.ln_c[0], L.ln_c[1], q.ln_eps, out16=h16, out32=h32)
+            S.ff_pre = K.gemm(h16, L.fi_w, bias=L.fi_b)
+            K.gelu_fwd(S.ff_pre, ff)
+            S.tmp_f = K.gemm(ff, L.fo_w, bias=L.fo_b, res=h32, out_dtype=F32)
+            K.norm(S.tmp_f, L.ln_f[0], L.ln_f[1], q.ln_eps, out16=h16, out32=h32)
+            tp.qf.append(S)
+        return h16
+
+    def _qformer_bwd(self, dh, tp):
+        """dh: fp32 [B*Q, hidden] gradient of the Q-Former output. Returns (dq32 [B*Q, hidden] gradient of the query
+        embeddings, d_ckv fp16 [B*N, n_cross*2*hidden] gradient of the fused cross-attention K/V projections)."""
+        q, W = self.d.qf, self.qfw
+        B, Q = tp.B, tp.Q
+        Hd, H = q.hidden, q.heads
+        dhd = Hd // H
+        N = self.d.vit.tokens
+        T = B * Q
+        scale = 1.0 / math.sqrt(dhd)
+        ldkv = tp.ckv.shape[1]
+        d_ckv = self._e(B * N, ldkv)
+        for L, S in zip(reversed(W.layers), reversed(tp.qf)):
+            d32, d16 = self._norm_bwd(S.tmp_f, dh, L.ln_f[0], q.ln_eps)
+            d_ff = K.gemm(d16, L.fo_w, w_mn_major=True)
+            K.gelu_bwd(S.ff_pre, d_ff, d_ff)
+            dh = K.gemm(d_ff, L.fi_w, w_mn_major=True, res=d32, out_dtype=F32)
+            if L.cross:
+                d32, d16 = self._norm_bwd(S.tmp_c, dh, L.ln_c[0], q.ln_eps)
+                d_ctx = K.gemm(d16, L.co_w, w_mn_major=True)
+                d_cq = self._e(T, Hd)
+                kk = tp.ckv[:, L.ckv_index * 2 * Hd:]
+                dkk = d_ckv[:, L.ckv_index * 2 * Hd:]
+                self._attn_bwd((S.cq, Hd, Q * Hd), (kk, ldkv, N * ldkv), (kk[:, Hd:], ldkv, N * ldkv), d_ctx,
+                               (d_cq, Hd, Q * Hd), (dkk, ldkv, N * ldkv), (dkk[:, Hd:], ldkv, N * ldkv), B, H, Q, N, dhd, scale,
+                               False, None)
+                dh = K.gemm(d_cq, L.cq_w, w_mn_major=True, res=d32, out_dtype=F32)
+            d32, d16 = self._norm_bwd(S.tmp_a, dh, L.ln_a[0], q.ln_eps)
+            d_ctx = K.gemm(d16, L.wo, w_mn_major=True)
+            dqkv = self._e(T, 3 * Hd)
+            st = (3 * Hd, Q * 3 * Hd)
+            self._attn_bwd((S.qkv, *st), (S.qkv[:, Hd:], *st), (S.qkv[:, 2 * Hd:], *st), d_ctx, (dqkv, *st), (dqkv[:, Hd:], *st),
+                           (dqkv[:, 2 * Hd:], *st), B, H, Q, Q, dhd, scale, False, None)
+            dh = K.gemm(dqkv, L.wqkv, w_mn_major=True, res=d32, out_dtype=F32)
+        dq32, _ = self._norm_bwd(tp.q_in, dh, W.emb_ln[0], q.ln_eps, want16=False)
+        return dq32, d_ckv
+
+    # ------------------------------------------------------------------------------ LLaMA with saved activations
+    def _llama_train_fwd(self, embeds32, kv_len, tp):
+        l, dev = self.d.llama, self.dev
+        B, S, D = embeds32.shape
+        H, dh, T = l.heads, l.head_dim, B * S
+        self._ensure_cache(B, S)
+        tp.pos = torch.arange(S, device=dev, dtype=torch.int32).repeat(B)
+        tp.kv_len, tp.S = kv_len, S
+        h = embeds32.reshape(T, D)
+        ctx, act = self._e(T, D), self._e(T, l.inter)
+        x2 = self._e(T, D)
+        tp.ll = []
+        for li, L in enumerate(self.llw.layers):
+            Sv = _Obj()
+            kc, vc = self.kcache[li], self.vcache[li]
+            Sv.h_in = h
+            Sv.x1 = self._e(T, D)
+            K.norm(h, L.n1, None, l.eps, rms=True, out16=Sv.x1)
+            Sv.qkv = K.gemm(Sv.x1, L.wqkv)
+            Sv.xa = None
+            if L.lora is not None:
+                r = self.d.lora_r
+                Sv.xa = K.gemm(Sv.x1, L.lora.a)
+                K.gemm(Sv.xa[:, :r], L.lora.bq, res=Sv.qkv[:, :D], out=Sv.qkv[:, :D], T=T, K=r, alpha=L.lora.scale)
+                K.gemm(Sv.xa[:, r:], L.lora.bv, res=Sv.qkv[:, 2 * D:], out=Sv.qkv[:, 2 * D:], T=T, K=r, alpha=L.lora.scale)
+            K.rope_cache(Sv.qkv, B, S, H, dh, tp.pos, self.llw.cos, self.llw.sin, kc, vc)
+            cs = (kc.stride(1), kc.stride(0), dh)
+            K.attention(Sv.qkv, kc, vc, ctx, B, H, S, S, dh, 1.0 / math.sqrt(dh), (3 * D, S * 3 * D, dh), cs, cs, (D, S * D, dh),
+                        causal=True, q_off=0, kv_len=kv_len)
+            Sv.h_mid = K.gemm(ctx, L.wo, res=h, out_dtype=F32)
+            K.norm(Sv.h_mid, L.n2, None, l.eps, rms=True, out16=x2)
+            Sv.gu = K.gemm(x2, L.wgu)
+            K.swiglu(Sv.gu, act, T, l.inter)
+            h = K.gemm(act, L.wd, res=Sv.h_mid, out_dtype=F32)
+            tp.ll.append(Sv)
+        tp.h_final = h
+        x16 = self._e(T, D)
+        K.norm(h, self.llw.norm, None, l.eps, rms=True, out16=x16)
+        return K.gemm(x16, self.llw.lm_head, out_dtype=F32)  # [T, V] fp32 (modeling_llama.py:690)
+
+    def _llama_train_bwd(self, dlogits16, tp, B):
+        """dlogits16 fp16 [T, V] (already multiplied by loss_scale) -> fp32 [T, D] gradient of inputs_embeds; LoRA A/B
+        gradients are written (unscaled) into the flat gradient buffer."""
+        l = self.d.llama
+        S, D, H, dh = tp.S, l.hidden, l.heads, l.head_dim
+        T = B * S
+        inv_scale = 1.0 / self.loss_scale
+        d_x = K.gemm(dlogits16, self.llw.lm_head, w_mn_major=True, out_dtype=F32)
+        dh32, dh16 = self._norm_bwd(tp.h_final, d_x, self.llw.norm, l.eps, rms=True)
+        att_scale = 1.0 / math.sqrt(dh)
+        for li in range(l.layers - 1, -1, -1):
+            L, Sv = self.llw.layers[li], tp.ll[li]
+            kc, vc = self.kcache[li], self.vcache[li]
+            d_act = K.gemm(dh16, L.wd, w_mn_major=True)
+            d_gu = self._e(T, 2 * l.inter)
+            K.swiglu_bwd(Sv.gu, d_act, d_gu, T, l.inter)
+            d_x2 = K.gemm(d_gu, L.wgu, w_mn_major=True, out_dtype=F32)
+            dmid32, dmid16 = self._norm_bwd(Sv.h_mid, d_x2, L.n2, l.eps, rms=True, add=dh32)
+            d_ctx = K.gemm(dmid16, L.wo, w_mn_major=True)
+            dqkv = self._e(T, 3 * D)
+            st = (3 * D, S * 3 * D)
+            cst = (kc.stride(1), kc.stride(0))
+            self._attn_bwd((Sv.qkv, *st), (kc, *cst), (vc, *cst), d_ctx, (dqkv, *st), (dqkv[:, D:], *st), (dqkv[:, 2 * D:], *st),
+                           B, H, S, S, dh, att_scale, True, tp.kv_len)
+            K.rope_bwd(dqkv, T, H, dh, tp.pos, self.llw.cos, self.llw.sin)
+            d_x1 = K.gemm(dqkv, L.wqkv, w_mn_major=True, out_dtype=F32)
+            if L.lora is not None:
+                r = self.d.lora_r
+                p = "llama_model.base_model.model.model.layers.%d.self_attn." % li
+                s = L.lora.scale
+                d_xa = self._e(T, 2 * r)
+                for j, (nm, b16, col) in enumerate((("q_proj", L.lora.bq, 0), ("v_proj", L.lora.bv, 2 * D))):
+                    dy = dqkv[:, col:col + D]
+                    # dB[d, r] = s * sum_t dy[t, d] * xa[t, r]
+                    K.gemm(dy, Sv.xa[:, j * r:], out=self.grad(p + nm + ".lora_B.default.weight"), x_mn_major=True, w_mn_major=True,
+                           T=D, F=r, K=T, ldx=3 * D, ldw=2 * r, bn_hint=128, alpha=s * inv_scale)
+                    # d_xa[t, r] = s * sum_d dy[t, d] * B[d, r]
+                    K.gemm(dy, b16, out=d_xa[:, j * r:], w_mn_major=True, T=T, F=r, K=D, ldx=3 * D, ldo=2 * r, alpha=s)
+                # dA[2r, D] = sum_t d_xa[t, :]^T x1[t, :]   (A_q and A_v are adjacent in the flat buffer)
+                o = self.segments[p + "q_proj.lora_A.default.weight"][0]
+                K.gemm(d_xa, Sv.x1, out=self.flat_grads[o:o + 2 * r * D].view(2 * r, D), x_mn_major=True, w_mn_major=True, T=2 * r, F=D,
+                       K=T, bn_hint=64, alpha=inv_scale)
+                K.gemm(d_xa, L.lora.a, w_mn_major=True, T=T, F=D, K=2 * r, res=d_x1, out=d_x1)
+            dh32, dh16 = self._norm_bwd(Sv.h_in, d_x1, L.n1, l.eps, rms=True, add=dmid32, want16=li > 0)
+        return dh32
+
+    # -------------------------------------------------------------------------------------------- training step
+    def forward_backward(self, image, maps, stage, ids_before, ids_after, text_ids, text_mask):
+        """Myriad.forward myriad.py:377-431 (host RNG choices made by the caller: `stage`, and which maps) + backward.
+        image fp32 [B,3,224,224], maps fp32 [B,1,224,224] (device); ids_* int64 prompt halves; text_ids int64 [B, Lt]
+        right-padded with eos, text_mask [B, Lt] 0/1 (CPU). Returns the loss (fp32 0-d device tensor); gradients of every
+        trainable parameter are left, unscaled, in `flat_grads` (parameters untouched by this stage stay zero)."""
+        d, l, dev = self.d, self.d.llama, self.dev
+        B, D = image.shape[0], l.hidden
+        inv_scale = 1.0 / self.loss_scale
+        K.memset_zero(self.flat_grads)
+        tp = self._tape = _Obj()
+        try:
+            emb = self.build_inputs_embeds(image, maps, stage, ids_before, ids_after, with_bos=True, text_ids=text_ids)
+        finally:
+            self._tape = None
+        Lt = text_ids.shape[1]
+        Ltot = emb.shape[1]
+        Lw = Ltot - Lt  # bos + wrapped image prompt
+        kv_len = (Lw + text_mask.sum(-1)).to(torch.int32).to(dev)
+        # targets myriad.py:406-416, shifted by one for next-token prediction (modeling_llama.py:697-703)
+        targets = torch.cat([torch.full((B, Lw), -100, dtype=torch.long), text_ids.masked_fill(text_ids == l.eos, -100)], 1)
+        shifted = torch.cat([targets[:, 1:], torch.full((B, 1), -100, dtype=torch.long)], 1).reshape(-1).to(dev)
+        logits = self._llama_train_fwd(emb, kv_len, tp)
+        T = B * Ltot
+        row_loss, stats, loss_out = self._e(T, dtype=F32), self._e(T, 2, dtype=F32), self._e(2, dtype=F32)
+        K.clamp_ce_fwd(logits, shifted, row_loss, stats, loss_out)
+        dlogits = self._e(T, l.vocab)
+        K.clamp_ce_bwd(logits, shifted, stats, loss_out, self.loss_scale, dlogits)
+        d_emb = self._llama_train_bwd(dlogits, tp, B)  # fp32 [T, D]
+        # ---- inputs_embeds -> image-token groups (myriad.py:249-266 concatenation order: Q-Former tokens, then VETokenizer)
+        n_before = 1 + ids_before.shape[-1]
+        flat = d_emb.reshape(-1)
+        base = n_before * D
+        Q = tp.Q
+        d_proj16 = self._cast16(flat[base:], Q, D, src_ld=D, src_gs=Ltot * D, groups=B)
+        if stage in (0, 1):
+            off = base + Q * D
+            K.colsum(flat[off:], D, Ltot * D, B, 1, 9 * D, self.grad("VETokenizer.base_prompts").reshape(-1), scale=inv_scale)
+            d_tok16 = self._cast16(flat[off + 9 * D:], 9, D, src_ld=D, src_gs=Ltot * D, groups=B)
+            self._ve_head_bwd(self.tokw, tp.tok, d_tok16, B)
+        d_h = K.gemm(d_proj16, self.qfw.proj_w, w_mn_major=True, out_dtype=F32)  # llama_proj is frozen: dX only
+        dq32, d_ckv = self._qformer_bwd(d_h, tp)
+        if stage in (1, 2):
+            Hq, nq0 = d.qf.hidden, d.qf.num_query
+            d_inst16 = self._cast16(dq32.reshape(-1)[nq0 * Hq:], 49, Hq, src_ld=Hq, src_gs=Q * Hq, groups=B)
+            self._ve_head_bwd(self.instw, tp.inst, d_inst16, B)
+        # cross-attention K/V -> ln_vision -> LoraAdaptorV2 weights (the ViT below is frozen: no dX)
+        d_enc = K.gemm(d_ckv, self.qfw.ckv_w, w_mn_major=True, out_dtype=F32)
+        d_pre, _ = self._norm_bwd(tp.ad_pre, d_enc, self.vitw.ln_vision[0], 1e-5, want16=False)
+        rows, Dv, rk = d_pre.shape[0], d.vit.dim, d.adaptor_rank
+        scratch = self._e(rows, 2 * rk, dtype=F32)
+        K.adaptor_bwd(tp.vit_x, d_pre, self.vitw.ad1, self.vitw.ad2, scratch, self.grad("expert_adaptor.conv1.weight"),
+                      self.grad("expert_adaptor.conv2.weight"), rows, Dv, rk, inv_scale)
+        return loss_out[0]
+
+    def optimizer_step(self, lr=None):
+        """DDP gradient averaging (runner_base.py:96-98: one all-reduce of the flat buffer over NCCL/NVLink) + fused AdamW
+        (runner_base.py:105-139) + refresh of the fp16 operand copies."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world > 1:
+            dist.all_reduce(self.flat_grads)
+        self.opt_step += 1
+        hp = self.hp
+        K.adamw_step(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.wd_mask, hp["lr"] if lr is None else lr,
+                     hp["beta1"], hp["beta2"], hp["eps"], hp["wd"], self.opt_step, inv_scale=1.0 / world, found_inf=self.found_inf)
+        self.refresh_trainables()
+
+    def train_step(self, image, maps, stage, ids_before, ids_after, text_ids, text_mask, lr=None):
+        loss = self.forward_backward(image, maps, stage, ids_before, ids_after, text_ids, text_mask)
+        self.optimizer_step(lr)
+        return loss

@@ -303,6 +303,17 @@ def myriad_loss(sd, image, maps, stage, ids_before, ids_after, text_ids, text_ma
     return clamp_ce_loss(logits, targets), logits
 
 
+def train_grads(sd, d, image, maps, stage, ids_b, ids_a, text, tmask):
+    """Loss + gradients of every trainable tensor (runner_base.py:111-119) by autograd over the oracle restatement."""
+    keys = [k for k in sd if k.startswith(("expert_adaptor.", "VEInstructor.", "VETokenizer.")) or ".lora_" in k]
+    sd2 = dict(sd)
+    for k in keys:
+        sd2[k] = sd[k].clone().requires_grad_(True)
+    loss, _ = myriad_loss(sd2, image, maps, stage, ids_b, ids_a, text, tmask, d)
+    loss.backward()
+    return loss.detach(), {k: (sd2[k].grad if sd2[k].grad is not None else torch.zeros_like(sd[k])) for k in keys}
+
+
 def greedy_generate(sd, inputs_embeds, d: MyriadDims, max_new_tokens=90, stop_seqs=((835,), (2277, 29937)),
                     min_new_tokens=1, return_margins=False):
     """Myriad.generate myriad.py:433-454 -> HF generate (third-party, unpinned; restated): greedy search over

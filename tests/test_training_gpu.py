@@ -1,0 +1,284 @@
+"""GPU: the training step (Myriad.forward + backward + AdamW, myriad.py:377-431 under base_task.py:233-271) on the C-ABI
+kernels against the CPU oracle's autograd and the committed golden gradients.
+
+tests/golden/myriad_mid_train*.npz were produced by oracle/gen_golden.py: with lora_r = 0 the UNMODIFIED reference modules
+ran under torch autograd and pinned the oracle's gradients (<= 1e-3 of each tensor's max); with lora_r = 8 peft is absent, so
+the LoRA gradients come from the restated oracle.
+
+Stated tolerance: the device backward uses fp16 tensor-core operands for activations AND activation gradients (loss scaled by
+1024, GradScaler semantics of runner_base.py:141-149) with fp32 accumulation; the oracle is fp32 throughout.
+  * loss:       |device - oracle| <= 2e-2 (absolute; the loss is ~14 because most synthetic targets sit on the 1e-7 clamp)
+  * gradients:  max |device - oracle| <= TOL_GRAD * max|oracle| per parameter tensor
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from myriad_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+TOL_GRAD = 3e-2
+TOL_UNIT = 1e-2
+
+
+@pytest.fixture(scope="module")
+def K():
+    from myriad_b200 import kernels
+    return kernels
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import myriad_oracle
+    return myriad_oracle
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    assert torch.isfinite(a).all(), "non-finite device values"
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20)
+
+
+def _sample(t, n=4096):  # same subsampling as oracle/gen_golden.py
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return f[::step][:n].clone()
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+def test_clamp_ce_fwd_bwd(K, O):
+    torch.manual_seed(0)
+    R, V = 37, 1000
+    logits = (torch.randn(R, V) * 3).requires_grad_(True)
+    labels = torch.randint(0, V, (R,))
+    labels[::5] = -100
+    logits.data[3, labels[3]] = 40.0   # p_y ~ 1 -> clamped high (zero gradient row)
+    logits.data[4, labels[4]] = -40.0  # p_y ~ 0 -> clamped low
+    p = O.softmax_lastdim(logits).clamp(1e-7, 1 - 1e-7)
+    keep = labels != -100
+    loss = -(torch.log(p)[keep, labels[keep]]).mean()
+    loss.backward()
+    lg = logits.detach().cuda()
+    lb = labels.cuda()
+    row_loss, stats, loss_out = torch.empty(R, device="cuda"), torch.empty(R, 2, device="cuda"), torch.empty(2, device="cuda")
+    K.clamp_ce_fwd(lg, lb, row_loss, stats, loss_out)
+    assert abs(loss_out[0].item() - loss.item()) < 1e-4 and int(loss_out[1].item()) == int(keep.sum())
+    dl = torch.empty(R, V, device="cuda", dtype=torch.float16)
+    K.clamp_ce_bwd(lg, lb, stats, loss_out, 64.0, dl)
+    e = rel(dl.float() / 64.0, logits.grad)
+    print("clamp-CE: loss %.5f, dlogits rel err %.2e" % (loss_out[0].item(), e))
+    assert e < 2e-3
+    assert dl[3].abs().max().item() == 0 and dl[4].abs().max().item() == 0 and dl[0].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("rms", [False, True])
+def test_norm_bwd(K, rms):
+    torch.manual_seed(1)
+    rows, D = 50, 1408 if not rms else 4096
+    x = torch.randn(rows, D, requires_grad=True)
+    g = torch.randn(D) * 0.1 + 1
+    dy = torch.randn(rows, D)
+    add = torch.randn(rows, D)
+    if rms:
+        y = g * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
+    else:
+        y = F.layer_norm(x, (D,), g, torch.zeros(D), 1e-5)
+    y.backward(dy)
+    out32 = torch.empty(rows, D, device="cuda")
+    out16 = torch.empty(rows, D, device="cuda", dtype=torch.float16)
+    K.norm_bwd(x.detach().cuda(), dy.cuda(), g.cuda(), 1e-6 if rms else 1e-5, rms=rms, add=add.cuda(), out32=out32, out16=out16)
+    e = rel(out32, x.grad + add)
+    print("norm_bwd rms=%s rel err %.2e" % (rms, e))
+    assert e < 1e-4 and rel(out16, x.grad + add) < 2e-3
+
+
+def test_swiglu_gelu_rope_bwd(K, O):
+    torch.manual_seed(2)
+    T, I = 33, 512
+    gu = torch.randn(T, 2 * I).half().float().requires_grad_(True)
+    da = torch.randn(T, I).half().float()
+    (F.silu(gu[:, :I]) * gu[:, I:]).backward(da)
+    dgu = torch.empty(T, 2 * I, device="cuda", dtype=torch.float16)
+    K.swiglu_bwd(gu.detach().half().cuda(), da.half().cuda(), dgu, T, I)
+    assert rel(dgu, gu.grad) < 3e-3
+    pre = torch.randn(T, I).half().float().requires_grad_(True)
+    O.gelu_erf(pre).backward(da)
+    dpre = torch.empty(T, I, device="cuda", dtype=torch.float16)
+    K.gelu_bwd(pre.detach().half().cuda(), da.half().cuda(), dpre)
+    assert rel(dpre, pre.grad) < 3e-3
+    out = torch.empty(T, I, device="cuda", dtype=torch.float16)
+    K.gelu_fwd(pre.detach().half().cuda(), out)
+    assert rel(out, O.gelu_erf(pre.detach())) < 2e-3
+    # rope backward: q, k thirds rotated back, v untouched
+    B, S, H, dh = 2, 9, 2, 128
+    D = H * dh
+    cos, sin = O.rope_tables(dh, 64)
+    pos = torch.arange(S)[None].expand(B, -1)
+    qkv = torch.randn(B, S, 3, H, dh).half().float().requires_grad_(True)
+    q = O.apply_rope(qkv[:, :, 0].transpose(1, 2), cos, sin, pos)
+    k = O.apply_rope(qkv[:, :, 1].transpose(1, 2), cos, sin, pos)
+    dq, dk, dv = (torch.randn(B, H, S, dh).half().float() for _ in range(3))
+    ((q * dq).sum() + (k * dk).sum() + (qkv[:, :, 2].transpose(1, 2) * dv).sum()).backward()
+    d = torch.stack([dq.transpose(1, 2), dk.transpose(1, 2), dv.transpose(1, 2)], 2).reshape(B * S, 3 * D).half().cuda().contiguous()
+    half = dh // 2
+    K.rope_bwd(d, B * S, H, dh, pos.reshape(-1).int().cuda(), cos[:, :half].contiguous().cuda(), sin[:, :half].contiguous().cuda())
+    e = rel(d, qkv.grad.reshape(B * S, 3 * D))
+    print("rope_bwd rel err %.2e" % e)
+    assert e < 3e-3
+
+
+@pytest.mark.parametrize("cfg", [dict(B=2, H=2, Sq=40, Skv=40, dh=128, causal=True, kv=(40, 33)),
+                                 dict(B=2, H=12, Sq=81, Skv=257, dh=64, causal=False, kv=None),
+                                 dict(B=1, H=3, Sq=81, Skv=81, dh=64, causal=False, kv=None)])
+def test_attention_bwd(cfg):
+    """Trainer._attn_bwd (batched tcgen05 GEMMs around the masked row softmax) against autograd."""
+    from myriad_b200.training import MyriadTrainer
+    torch.manual_seed(3)
+    B, H, Sq, Skv, dh = cfg["B"], cfg["H"], cfg["Sq"], cfg["Skv"], cfg["dh"]
+    HD = H * dh
+    scale = 1.0 / math.sqrt(dh)
+    q = torch.randn(B, Sq, H, dh).half().float().requires_grad_(True)
+    k = torch.randn(B, Skv, H, dh).half().float().requires_grad_(True)
+    v = torch.randn(B, Skv, H, dh).half().float().requires_grad_(True)
+    do = torch.randn(B, Sq, H, dh).half().float()
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    mask = torch.zeros(B, 1, Sq, Skv, dtype=torch.bool)
+    if cfg["causal"]:
+        mask |= (torch.arange(Skv)[None, :] > torch.arange(Sq)[:, None])[None, None]
+    if cfg["kv"] is not None:
+        for b, n in enumerate(cfg["kv"]):
+            mask[b, :, :, n:] = True
+    p = torch.softmax(s.masked_fill(mask, float("-inf")), -1)
+    o = torch.einsum("bhqk,bkhd->bqhd", p, v)
+    o.backward(do)
+    tr = MyriadTrainer.__new__(MyriadTrainer)
+    tr.dev = torch.device("cuda:0")
+    c = lambda t: t.detach().reshape(-1, HD).half().cuda().contiguous()
+    qd, kd, vd, dod = c(q), c(k), c(v), c(do)
+    dq, dk, dv = torch.zeros_like(qd), torch.zeros_like(kd), torch.zeros_like(vd)
+    kv_len = torch.tensor(cfg["kv"], dtype=torch.int32, device="cuda") if cfg["kv"] is not None else None
+    tr._attn_bwd((qd, HD, Sq * HD), (kd, HD, Skv * HD), (vd, HD, Skv * HD), dod, (dq, HD, Sq * HD), (dk, HD, Skv * HD),
+                 (dv, HD, Skv * HD), B, H, Sq, Skv, dh, scale, cfg["causal"], kv_len)
+    eq, ek, ev = rel(dq, q.grad.reshape(-1, HD)), rel(dk, k.grad.reshape(-1, HD)), rel(dv, v.grad.reshape(-1, HD))
+    print("attention bwd %s: dq %.2e dk %.2e dv %.2e" % (cfg, eq, ek, ev))
+    assert max(eq, ek, ev) < TOL_UNIT
+
+
+def test_conv_trunk_fwd_bwd(K, O):
+    """VEInstructor conv stack + 1x1 head: forward and every weight/bias gradient against autograd (networks.py:98-127)."""
+    from myriad_b200.training import MyriadTrainer
+    d = syn.mid_dims()
+    sd = syn.make_state_dict(d, 0)
+    tr = MyriadTrainer(sd, d, device="cuda:0", max_batch=2, max_seq=64, loss_scale=1.0)
+    _, maps = syn.make_inputs(2, seed=12)
+    keys = [k for k in sd if k.startswith("VEInstructor.")]
+    sd2 = dict(sd)
+    for k in keys:
+        sd2[k] = sd[k].clone().requires_grad_(True)
+    ref = O.ve_instructor(sd2, maps)  # [B, 49, 768]
+    dout = torch.randn(ref.shape).half().float()
+    ref.backward(dout)
+    tp = type("T", (), {})()
+    trunk, tp.saved = tr._conv_trunk_train(maps.cuda(), tr.instw)
+    tp.head_in = trunk.reshape(2 * 49, 1024)
+    out = K.gemm(tp.head_in, tr.instw.head_w, bias=tr.instw.head_b, out_dtype=torch.float32)
+    assert rel(out.reshape(2, 49, 768), ref.detach()) < 2e-3
+    K.memset_zero(tr.flat_grads)
+    tr._ve_head_bwd(tr.instw, tp, dout.reshape(-1, 768).half().cuda().contiguous(), 2)
+    grads = tr.export_grads()
+    worst = 0.0
+    for k in keys:
+        e = rel(grads[k], sd2[k].grad)
+        worst = max(worst, e)
+        print("  conv grad %-34s rel err %.2e" % (k, e))
+    assert worst < TOL_GRAD
+
+
+def test_adamw_matches_torch(K):
+    torch.manual_seed(5)
+    n = 10000
+    p0, g = torch.randn(n), torch.randn(n) * 0.01
+    mask = (torch.arange(n) % 3 != 0)
+    pa = torch.nn.Parameter(p0[mask].clone())
+    pb = torch.nn.Parameter(p0[~mask].clone())
+    opt = torch.optim.AdamW([{"params": [pa], "weight_decay": 0.05}, {"params": [pb], "weight_decay": 0.0}], lr=1e-3, betas=(0.9, 0.999))
+    p = p0.clone().cuda()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    found = torch.zeros(1, device="cuda", dtype=torch.int32)
+    for step in (1, 2, 3):
+        pa.grad, pb.grad = g[mask].clone(), g[~mask].clone()
+        opt.step()
+        K.adamw_step(p, (g * 8).cuda(), m, v, mask.to(torch.uint8).cuda(), 1e-3, 0.9, 0.999, 1e-8, 0.05, step, inv_scale=1 / 8.0, found_inf=found)
+    ref = p0.clone()
+    ref[mask], ref[~mask] = pa.data, pb.data
+    assert rel(p, ref) < 1e-5
+    bad = (g * 8).cuda()
+    bad[7] = float("inf")
+    before = p.clone()
+    K.adamw_step(p, bad, m, v, mask.to(torch.uint8).cuda(), 1e-3, 0.9, 0.999, 1e-8, 0.05, 4, inv_scale=1 / 8.0, found_inf=found)
+    assert int(found.item()) == 1 and torch.equal(p, before), "inf gradient must skip the update (GradScaler.step)"
+
+
+# ------------------------------------------------------------------------------------------- full training step
+@pytest.mark.parametrize("lora_r", [0, 8])
+def test_train_step_grads_vs_golden(golden, lora_r):
+    from myriad_b200.training import MyriadTrainer
+    g = golden("myriad_mid_train" + ("_lora" if lora_r else ""))
+    d = syn.mid_dims(lora_r=lora_r)
+    sd = syn.make_state_dict(d, int(g["seed"]))
+    image, maps = syn.make_inputs(2, seed=int(g["input_seed"]))
+    ids_b, ids_a = syn.make_prompt_ids(d.llama.vocab)
+    text, tmask = torch.from_numpy(g["text"]), torch.from_numpy(g["text_mask"])
+    tr = MyriadTrainer(sd, d, device="cuda:0", max_batch=2, max_seq=256)
+    for stage in (1, 0, 2):
+        loss = tr.forward_backward(image.cuda(), maps.cuda(), stage, ids_b, ids_a, text, tmask)
+        ref_loss = float(g["loss_stage%d" % stage])
+        grads = tr.export_grads()
+        worst, worst_k = 0.0, None
+        for k, t in grads.items():
+            ref = torch.from_numpy(g["s%d:%s" % (stage, k)])
+            if ref.abs().max() == 0:
+                assert t.abs().max().item() == 0, "%s must stay zero in stage %d (unused parameter)" % (k, stage)
+                continue
+            e = rel(_sample(t), ref)
+            if e > worst:
+                worst, worst_k = e, k
+        print("train step lora_r=%d stage %d: loss %.5f (oracle %.5f), worst grad rel err %.2e (%s)" % (
+            lora_r, stage, loss.item(), ref_loss, worst, worst_k))
+        assert abs(loss.item() - ref_loss) < 2e-2
+        assert worst < TOL_GRAD, worst_k
+
+
+def test_train_step_vs_live_oracle_and_update(O, golden):
+    """One full step against the oracle's autograd on fresh inputs (not the golden ones), then the optimizer update against
+    torch.optim.AdamW fed the oracle's gradients."""
+    from myriad_b200.training import MyriadTrainer
+    d = syn.mid_dims(lora_r=8)
+    sd = syn.make_state_dict(d, 2)
+    image, maps = syn.make_inputs(2, seed=77)
+    ids_b, ids_a = syn.make_prompt_ids(d.llama.vocab)
+    gen = torch.Generator().manual_seed(3)
+    text = torch.randint(3, d.llama.vocab, (2, 8), generator=gen)
+    tmask = torch.ones(2, 8, dtype=torch.long)
+    text[0, 6:] = d.llama.eos
+    tmask[0, 6:] = 0
+    oloss, ograds = O.train_grads(sd, d, image, maps, 1, ids_b, ids_a, text, tmask)
+    tr = MyriadTrainer(sd, d, device="cuda:0", max_batch=2, max_seq=256, lr=1e-3, weight_decay=0.05)
+    loss = tr.forward_backward(image.cuda(), maps.cuda(), 1, ids_b, ids_a, text, tmask)
+    grads = tr.export_grads()
+    worst = max(rel(grads[k], ograds[k]) for k in ograds if ograds[k].abs().max() > 0)
+    print("live oracle: loss %.5f vs %.5f, worst grad rel err %.2e" % (loss.item(), oloss.item(), worst))
+    assert abs(loss.item() - oloss.item()) < 2e-2 and worst < TOL_GRAD
+    # AdamW step 1: update = -lr * sign-like(g); compare parameters after the step with torch's AdamW on the device grads
+    before = tr.export_state_dict()
+    tr.optimizer_step()
+    after = tr.export_state_dict()
+    for k in ("VETokenizer.meta_net.15.weight", "VEInstructor.meta_net.0.bias", "expert_adaptor.conv1.weight"):
+        p = torch.nn.Parameter(before[k].cpu().clone())
+        p.grad = grads[k].cpu().clone()
+        wd = 0.05 if (p.ndim >= 2 and "bias" not in k) else 0.0
+        torch.optim.AdamW([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd).step()
+        assert rel(after[k], p.data) < 1e-5, k
