@@ -197,16 +197,17 @@ def roofline_probe(eng, dims, dev, peaks):
     B = BATCH
     x = torch.randn(B, l.hidden, device=dev).half()
     a = torch.randn(B, l.inter, device=dev).half()
-    qkv = torch.empty(B, 3 * l.hidden, device=dev, dtype=torch.float16)
-    o = torch.empty(B, l.hidden, device=dev, dtype=torch.float32)
-    gu = torch.empty(B, 2 * l.inter, device=dev, dtype=torch.float16)
+    wq = eng.llw.layers[0].wqkv.shape[0]  # 3 * hidden + 2 * lora_r (LoRA A rows ride along)
+    qkv = torch.empty(B, wq, device=dev, dtype=torch.float16)
+    o = torch.zeros(B, l.hidden, device=dev, dtype=torch.float32)
+    act = torch.empty(B, l.inter, device=dev, dtype=torch.float16)
 
     def sweep():
         for L in eng.llw.layers:
-            K.gemm(x, L.wqkv, out=qkv)
-            K.gemm(x, L.wo, res=o, out=o)
-            K.gemm(x, L.wgu, out=gu)
-            K.gemm(a, L.wd, res=o, out=o)
+            K.gemm(x, L.wqkv, out=qkv, w_static=True)
+            K.gemm(x, L.wo, res=o, out=o, w_static=True)
+            K.gemm(x, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
+            K.gemm(a, L.wd, res=o, out=o, w_static=True)
 
     for _ in range(2):
         sweep()
@@ -220,11 +221,12 @@ def roofline_probe(eng, dims, dev, peaks):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     n_launch = 4 * l.layers
-    wbytes = l.layers * 2 * (3 * l.hidden * l.hidden + l.hidden * l.hidden + 2 * l.inter * l.hidden + l.hidden * l.inter)
-    abytes = l.layers * B * (2 * 2 * l.hidden + 2 * l.inter + 2 * 3 * l.hidden + 8 * l.hidden + 4 * l.inter + 8 * l.hidden)
+    wbytes = l.layers * 2 * (wq * l.hidden + l.hidden * l.hidden + 2 * l.inter * l.hidden + l.hidden * l.inter)
+    # activations per layer: x read 3x (fp16), act read once, qkv / act written (fp16), fp32 residual read + written twice
+    abytes = l.layers * B * (3 * 2 * l.hidden + 2 * l.inter + 2 * wq + 2 * l.inter + 2 * 8 * l.hidden)
     per_launch = (wbytes + abytes) / n_launch
     achieved = (wbytes + abytes) / (ms / 1e3) / 1e9
-    roof = {"kernel": "gemm_tc_kernel (decode, T=%d: qkv/o/gate_up/down of all 32 layers)" % B, "bound": "hbm", "achieved": achieved,
+    roof = {"kernel": "gemm_tc_kernel (decode, T=%d: qkv+loraA / o+res / gate_up+swiglu / down+res of all 32 layers)" % B, "bound": "hbm", "achieved": achieved,
             "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
             "avg_launch_us": ms * 1e3 / n_launch, "algorithmic_bytes_per_launch": per_launch}
     # tensor-bound context: the ViT MLP GEMMs at the bench batch (T = B * 257)

@@ -34,7 +34,7 @@ enum myr_status {
   MYR_ERR_WORKSPACE = -4 /* workspace too small */
 };
 enum myr_dtype { MYR_F16 = 0, MYR_F32 = 1 };
-enum myr_act { MYR_ACT_NONE = 0, MYR_ACT_GELU_ERF = 1, MYR_ACT_RELU = 2 };
+enum myr_act { MYR_ACT_NONE = 0, MYR_ACT_GELU_ERF = 1, MYR_ACT_RELU = 2, MYR_ACT_SWIGLU = 3 };
 
 /* ---- library ------------------------------------------------------------------------------------- */
 int myr_version(void);                            /* ABI version (integer, bumps on breaking change) */
@@ -53,7 +53,14 @@ unsigned long long myr_launch_count(void);        /* kernels launched (or captur
  *                           = 1: operand stored [K, rows] (rows contiguous) — used by dgrad/wgrad.
  * Epilogue order (each step optional): v = acc (+ bias[f]); if round_acc: v = fp16(v);
  *   if f < scale_cols: v = fp16(v * scale); if act: v = fp16(act(v)); v *= alpha; if res: v += res[t, f]; store as out_dtype.
- * Alignment: x, w, out 16-byte aligned; ldx, ldw (and batch strides) multiples of 8 elements.
+ * act = MYR_ACT_SWIGLU (modeling_llama.py:139-140 fused into the gate/up projection): W holds gate and up rows
+ *   interleaved in blocks of 64 ([gate 0..63 | up 0..63 | gate 64..127 | ...], F = 2 * I rows) and the kernel writes
+ *   out[t, i] = silu(fp16(gate_i)) * fp16(up_i) for i < I (fp16, no bias / residual).
+ * Alignment: x, w 16-byte aligned; ldx, ldw (and batch strides) multiples of 8 elements; out / res / bias use 16-byte
+ *   vector accesses when their pointers and strides allow it, scalar accesses otherwise.
+ * Workspace: COUNTERS (first 64 KiB, int32, MUST be zero when first handed to the library; the library leaves them zero)
+ *   followed by fp32 partial tiles of split tiles ("stream-K": every CTA gets an equal, contiguous range of k-blocks; a
+ *   tile shared by several CTAs is finished, deterministically, by the last one to arrive).
  */
 typedef struct {
   const void* x; int64_t ldx;
@@ -74,9 +81,13 @@ typedef struct {
   int32_t nb0, nb1;            /* batched GEMM over nb0 x nb1 independent problems (0 = 1): attention backward per (batch, head) */
   int64_t x_bs0, x_bs1, w_bs0, w_bs1, o_bs0, o_bs1; /* element strides of the two batch dims; no residual / split-K when batched */
   int32_t alpha_set; float alpha; /* if alpha_set: v *= alpha (fp32, unrounded) after the activation, before the residual add */
+  int32_t pdl;                 /* launch with programmatic stream serialization (overlaps the previous kernel's tail) */
+  int32_t w_static;            /* w is not written by any kernel in flight: its tiles may be prefetched before the PDL wait */
 } myr_gemm_args;
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);
 int myr_gemm_f16(const myr_gemm_args* args, void* stream);
+/* Programmatic dependent launch on/off for the whole library (default on; env MYR_PDL=0 disables). */
+void myr_set_pdl(int32_t enabled);
 
 /* ---- attention (tcgen05 flash forward) ---------------------------------------------------------------
  * out[b, i, h, :] = softmax_j(scale * q[b,i,h,:] . k[b,j,h,:] + mask) v[b,j,h,:], fp16 in/out, fp32 softmax.
@@ -130,8 +141,31 @@ typedef struct {
   const void* cos_table; const void* sin_table;
   void* kcache; void* vcache; int64_t cache_token_stride, cache_batch_stride;
   int32_t cache_off; const void* cache_off_dev;
+  /* optional fused peft LoRA on q_proj / v_proj (myriad.py:171-178; third-party peft semantics y += (alpha/r) B (A x)):
+   * the fused qkv GEMM carries the 2r rows of A_q, A_v after the 3*H*dh qkv rows, so xa = x A^T arrives in columns
+   * [3*H*dh, 3*H*dh + 2r) of each qkv row; this kernel adds lora_scale * B xa to q and v before rotating / caching. r = 8. */
+  const void* lora_bq; const void* lora_bv; int32_t lora_r; float lora_scale;
 } myr_rope_args;
 int myr_rope_cache(const myr_rope_args* args, void* stream);
+
+/* ---- decode-step attention (one new token per sequence): LoRA-B + RoPE + KV-cache append + attention over the cache
+ * in ONE launch, one CTA per (head, batch row). Replaces, for Sq = 1, modeling_llama.py:109-123 (rotary), :190-195 (cache
+ * growth by torch.cat), :197-215 (scores / fp32 softmax / PV) and the peft LoRA update of q and v (myriad.py:171-178).
+ * qkv: [B, ldq] fp16 rows q | k | v | xa_q | xa_v (see myr_rope_args). The new k / v are written to cache slot
+ * cache_off (or *cache_off_dev) of each batch row; kv_len[b] = visible keys including the new one. dh must be 128. */
+typedef struct {
+  const void* qkv; int64_t ldq;
+  int32_t B, H, dh;
+  const void* pos;                       /* int32 [B] */
+  const void* cos_table; const void* sin_table;
+  void* kcache; void* vcache; int64_t cache_token_stride, cache_batch_stride; int32_t cache_len;
+  int32_t cache_off; const void* cache_off_dev;
+  const void* kv_len;                    /* int32 [B] device */
+  const void* lora_bq; const void* lora_bv; int32_t lora_r; float lora_scale;
+  float scale;
+  void* out; int64_t ldo;                /* fp16 [B, H * dh] */
+} myr_decode_attn_args;
+int myr_decode_attention(const myr_decode_attn_args* args, void* stream);
 
 /* SwiGLU modeling_llama.py:139-140: out[t, i] = silu(gate_up[t, i]) * gate_up[t, I + i] (fp16). */
 int myr_swiglu(const void* gate_up, int64_t ld_gu, void* out, int64_t ld_out, int32_t T, int32_t I, void* stream);

@@ -84,6 +84,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // q / k / v (and kv_len) come from the previous kernels
+  pdl_launch_dependents();
   const uint32_t t_s = tmem_base + (uint32_t(warp * 32) << 16);
   const uint32_t t_o = t_s + (uint32_t)p.ocol;
 
@@ -324,11 +326,11 @@ extern "C" int myr_attention_fwd(const myr_attn_args* a, void* stream_) {
     attr_set = true;
   }
   if (nch <= 2)
-    attn_fwd_kernel<2><<<grid, 128, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
+    MYR_CHECK_CUDA(launch_kernel(attn_fwd_kernel<2>, grid, dim3(128), smem_bytes, stream, true, tmQ, tmK, tmV, p));
   else if (nch == 3)
-    attn_fwd_kernel<3><<<grid, 128, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
+    MYR_CHECK_CUDA(launch_kernel(attn_fwd_kernel<3>, grid, dim3(128), smem_bytes, stream, true, tmQ, tmK, tmV, p));
   else
-    attn_fwd_kernel<4><<<grid, 128, smem_bytes, stream>>>(tmQ, tmK, tmV, p);
+    MYR_CHECK_CUDA(launch_kernel(attn_fwd_kernel<4>, grid, dim3(128), smem_bytes, stream, true, tmQ, tmK, tmV, p));
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }

@@ -16,6 +16,16 @@ void set_error(const char* fmt, ...) {
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("MYR_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(int v) { g_pdl = v ? 1 : 0; }
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -85,6 +95,8 @@ int myr_last_error(char* buf, size_t n) {
   buf[n - 1] = 0;
   return MYR_OK;
 }
+
+void myr_set_pdl(int32_t enabled) { myr::set_pdl(enabled); }
 
 int myr_device_sm_count(void) { return myr::sm_count(); }
 

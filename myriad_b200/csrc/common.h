@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/myriad_b200.h"
 
@@ -42,6 +43,28 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
     myr::count_launch();                  \
     MYR_CHECK_CUDA(cudaGetLastError());   \
   } while (0)
+
+// Programmatic dependent launch switch for the whole library (myr_set_pdl / env MYR_PDL=0).
+bool pdl_enabled();
+void set_pdl(int v);
+
+// Launch through cudaLaunchKernelEx; with `pdl` (and the library switch on) the kernel carries the programmatic stream
+// serialization attribute. Only kernels that execute pdl_wait() before their first dependent access may pass pdl = true.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                        Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,15 +1,27 @@
 // tcgen05 + TMA GEMM for sm_100a:  out[t, f] = epilogue( sum_k X[t, k] * W[f, k] ).
 //
-// Layout choice ("features on lanes"): the weight tile (128 features) is the UMMA A operand, so each of
-// the 128 TMEM lanes holds one output feature; the token tile (BN = 16..256 tokens) is the UMMA N side.
-// The same kernel therefore covers decode (T <= 32: weight streaming, HBM-bound, split-K over the SMs)
-// and prefill / ViT (T in the thousands: tensor-bound, BN up to 256 => 128x256x16 MMAs at full rate).
+// One persistent, warp-specialised kernel (320 threads, 1 CTA / SM) in two operand arrangements:
+//   * "lanes = features" (T <= 64: decode / weight streaming, HBM-bound): the 128-row UMMA A tile is a weight tile, the
+//     token tile (BN = 16..64) is the UMMA N side. Every byte of W is read exactly once.
+//   * "lanes = tokens"   (T  > 64: prefill / ViT / training, tensor-bound): A = 128 tokens, B = BN <= 256 features, so an
+//     epilogue thread owns one token row and 16 consecutive features per TMEM load: bias / residual / output move as
+//     16-byte vectors.
+// Warp roles:
+//   warp 0    : TMA producer   (global -> 128B-swizzled smem ring, up to 8 stages, mbarrier complete_tx)
+//   warp 1    : MMA issuer     (one thread issues tcgen05.mma; tcgen05.commit frees smem stages / publishes TMEM)
+//   warps 2-9 : epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> global), two warps per TMEM lane quarter
+// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of one segment overlap the MMAs of the next.
 //
-// Persistent, warp-specialised CTA (192 threads, 1 CTA / SM):
-//   warp 0   : TMA producer   (global -> 128B-swizzled smem ring, up to 8 stages, mbarrier complete_tx)
-//   warp 1   : MMA issuer     (one thread issues tcgen05.mma; tcgen05.commit frees smem stages / publishes TMEM)
-//   warps 2-5: epilogue       (tcgen05.ld TMEM -> registers -> fused epilogue -> coalesced global stores)
-// Two TMEM accumulator stages (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Work decomposition ("stream-K"): the (tile, k-block) space is cut into one contiguous range of `per` k-blocks per CTA.
+// `per` a multiple of the k-blocks per tile gives the classic data-parallel schedule; otherwise ranges cross tile
+// borders, every CTA gets the same number of k-blocks (no wave quantisation when 172 weight tiles meet 148 SMs) and a
+// tile covered by several CTAs is finished by whichever CTA arrives last: partial accumulators go to the workspace, an
+// arrival counter per tile elects the finisher, which sums the partials in segment order (deterministic) and runs the
+// fused epilogue. The counters live at the head of the workspace, start at zero and are reset by the finisher.
+//
+// Programmatic dependent launch: the kernel releases its dependents at once and waits for its own predecessor only
+// before it touches activations; with `w_static` the producer streams the first ring of WEIGHT tiles before that wait, so
+// weight prefetch overlaps the tail of the previous kernel.
 //
 // Replaces the cuBLAS calls behind nn.Linear in the reference hot path (see include/myriad_b200.h).
 #include "common.h"
@@ -17,14 +29,19 @@
 
 namespace myr {
 
-constexpr int BM = 128;       // features per tile (UMMA M)
+constexpr int BM = 128;       // rows of the A tile (UMMA M)
 constexpr int BK = 64;        // halfs per k-block = one 128-byte swizzle row
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int SMEM_TILE_BUDGET = 192 * 1024;
-constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_TILE_BUDGET = 192 * 1024;      // 1 CTA / SM (lanes = tokens)
+constexpr int SMEM_TILE_BUDGET_OCC2 = 108 * 1024;  // 2 CTAs / SM (lanes = features): the next kernel's CTA moves in early
+constexpr int N_EPI_WARPS = 8;
+constexpr int EPI_THREADS = 32 * N_EPI_WARPS;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STAGE_COLS = 256;
+constexpr size_t COUNTER_BYTES = 64 * 1024;  // head of the workspace: int32 arrival counters, one per split tile
+constexpr int MAX_COUNTERS = (int)(COUNTER_BYTES / 4);
 
 struct Epilogue {
   const __half* bias;
@@ -41,43 +58,206 @@ struct Epilogue {
   float alpha;             // fp32 scale applied after the activation, before the residual (gradient unscale, LoRA alpha/r)
   int group_rows;          // 0 = plain rows; else out row t lives at (t / group_rows) * group_stride + (t % group_rows) * ldo
   long long group_stride;
+  int vec;                 // 16-byte vector access to bias / res / out is legal (alignment checked on the host)
 };
 
 struct GemmKernelParams {
   int T, F, K;
-  int BN, n_tt, n_ft, ksplit, kb_total, kb_per_split;
+  int row_mode;            // 1: lanes = tokens (A = X), 0: lanes = features (A = W)
+  int BN, n_mt, n_nt, kb_total;
+  long long total_kb;      // n_tiles * kb_total
+  int per;                 // k-blocks per CTA range
+  int max_seg;             // partial slots per tile
   int num_stages, stage_bytes;
-  int x_mn, w_mn;
+  int a_mn, b_mn;
   uint32_t idesc;
-  float* partial;  // [ksplit][T][F] fp32 when ksplit > 1
+  float* partial;
+  int* counters;
   int nb1, nbatch;                 // batched mode: batch index bidx -> (b0 = bidx / nb1, b1 = bidx % nb1)
   long long o_bs0, o_bs1;          // output element strides of the two batch dims
+  int w_static;
+  int tmem_cols, acc_stride;       // TMEM columns allocated by this CTA, columns between the two accumulator stages
   Epilogue ep;
 };
 
-__device__ __forceinline__ void epilogue_store(const Epilogue& ep, float v, float bias_f, long long t, int f,
-                                               long long boff = 0) {
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+// erf with |abs error| <= 1.5e-7 (Abramowitz-Stegun 7.1.26): well below the fp16 rounding applied to every GELU output.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float y = fmaf(-p * t, e, 1.0f);
+  return copysignf(y, x);
+}
+
+// element-wise part of the epilogue, up to (not including) the residual add
+__device__ __forceinline__ float epi_transform(const Epilogue& ep, float v, float bias_f, int f) {
   v += bias_f;
   if (ep.round_acc) v = round_f16(v);
   if (f < ep.scale_cols) v = round_f16(v * ep.scale);
-  if (ep.act == MYR_ACT_GELU_ERF) v = round_f16(gelu_erf(v));
+  if (ep.act == MYR_ACT_GELU_ERF) v = round_f16(0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752440f)));
   else if (ep.act == MYR_ACT_RELU) v = fmaxf(v, 0.f);
-  v *= ep.alpha;
+  return v * ep.alpha;
+}
+
+__device__ __forceinline__ long long out_row_offset(const Epilogue& ep, long long t) {
+  return ep.group_rows ? (t / ep.group_rows) * ep.group_stride + (t % ep.group_rows) * ep.ldo : t * ep.ldo;
+}
+
+__device__ __forceinline__ void epi_store_scalar(const Epilogue& ep, float v, long long t, int f, long long boff) {
   if (ep.res) {
-    float r = (ep.res_dtype == MYR_F32) ? reinterpret_cast<const float*>(ep.res)[t * ep.ldr + f]
-                                        : __half2float(reinterpret_cast<const __half*>(ep.res)[t * ep.ldr + f]);
-    v += r;
+    v += (ep.res_dtype == MYR_F32) ? reinterpret_cast<const float*>(ep.res)[t * ep.ldr + f]
+                                   : __half2float(reinterpret_cast<const __half*>(ep.res)[t * ep.ldr + f]);
   }
-  const long long o = boff + (ep.group_rows ? (t / ep.group_rows) * ep.group_stride + (t % ep.group_rows) * ep.ldo + f
-                                            : t * ep.ldo + f);
+  const long long o = boff + out_row_offset(ep, t) + f;
   if (ep.out_dtype == MYR_F32)
     reinterpret_cast<float*>(ep.out)[o] = v;
   else
     reinterpret_cast<__half*>(ep.out)[o] = __float2half_rn(v);
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+__device__ __forceinline__ void unpack8h(const uint4 u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 p = __half22float2(h[i]);
+    f[2 * i] = p.x;
+    f[2 * i + 1] = p.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8h(const float* f) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// lanes = tokens: this thread owns token t; v[0..16) are features f0 .. f0+15 of that token (already summed over k).
+__device__ __forceinline__ void epi_row16(const Epilogue& ep, float* v, long long t, int f0, int F, long long obase) {
+  if (ep.vec && f0 + 16 <= F) {
+    float b[16];
+    if (ep.bias) {
+      const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + f0);
+      unpack8h(__ldg(bp), b);
+      unpack8h(__ldg(bp + 1), b + 8);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) b[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = epi_transform(ep, v[j], b[j], f0 + j);
+    if (ep.res) {
+      if (ep.res_dtype == MYR_F32) {
+        const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.res) + t * ep.ldr + f0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 r = rp[j];
+          v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+      } else {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(ep.res) + t * ep.ldr + f0);
+        float r[16];
+        unpack8h(rp[0], r);
+        unpack8h(rp[1], r + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += r[j];
+      }
+    }
+    if (ep.out_dtype == MYR_F32) {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + obase + f0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ep.out) + obase + f0);
+      op[0] = pack8h(v);
+      op[1] = pack8h(v + 8);
+    }
+  } else {
+    for (int j = 0; j < 16; ++j) {
+      const int f = f0 + j;
+      if (f >= F) break;
+      float x = epi_transform(ep, v[j], ep.bias ? __half2float(ep.bias[f]) : 0.f, f);
+      if (ep.res) {
+        x += (ep.res_dtype == MYR_F32) ? reinterpret_cast<const float*>(ep.res)[t * ep.ldr + f]
+                                       : __half2float(reinterpret_cast<const __half*>(ep.res)[t * ep.ldr + f]);
+      }
+      if (ep.out_dtype == MYR_F32)
+        reinterpret_cast<float*>(ep.out)[obase + f] = x;
+      else
+        reinterpret_cast<__half*>(ep.out)[obase + f] = __float2half_rn(x);
+    }
+  }
+}
+
+// SwiGLU pair (modeling_llama.py:139-140) with the rounding points of the unfused path: gate / up rounded to fp16 first.
+__device__ __forceinline__ float swiglu_pair(float g, float u) {
+  g = round_f16(g);
+  u = round_f16(u);
+  return silu_f(g) * u;
+}
+
+// lanes = tokens, SwiGLU: g[16] / u[16] are gate / up features i0..i0+15 of token t; writes out[t, i0..i0+15] (fp16).
+__device__ __forceinline__ void epi_row16_swiglu(const Epilogue& ep, const float* g, const float* u, int i0, int I, long long obase) {
+  float o[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = swiglu_pair(g[j], u[j]);
+  __half* op = reinterpret_cast<__half*>(ep.out) + obase + i0;
+  if (ep.vec && i0 + 16 <= I) {
+    reinterpret_cast<uint4*>(op)[0] = pack8h(o);
+    reinterpret_cast<uint4*>(op)[1] = pack8h(o + 8);
+  } else {
+    for (int j = 0; j < 16 && i0 + j < I; ++j) op[j] = __float2half_rn(o[j]);
+  }
+}
+
+struct Seg {
+  int tile, kb0, kb1;
+};
+// next segment of the contiguous k-block range [g, g1): stays inside one tile
+__device__ __forceinline__ Seg next_seg(long long& g, long long g1, int kb_total) {
+  Seg s;
+  s.tile = (int)(g / kb_total);
+  s.kb0 = (int)(g - (long long)s.tile * kb_total);
+  const long long room = g1 - g;
+  s.kb1 = (room < (long long)(kb_total - s.kb0)) ? s.kb0 + (int)room : kb_total;
+  g += s.kb1 - s.kb0;
+  return s;
+}
+
+struct TileCoord {
+  int m0, n0, b0, b1, bidx;
+};
+__device__ __forceinline__ TileCoord tile_coord(const GemmKernelParams& p, int tile) {
+  TileCoord c;
+  const int per_batch = p.n_mt * p.n_nt;
+  c.bidx = tile / per_batch;
+  const int rem = tile - c.bidx * per_batch;
+  int mt, nt;
+  if (p.row_mode) {  // CTAs running side by side share the weight (B) tile and walk the token tiles
+    nt = rem / p.n_mt;
+    mt = rem - nt * p.n_mt;
+  } else {
+    mt = rem / p.n_nt;
+    nt = rem - mt * p.n_nt;
+  }
+  c.m0 = mt * BM;
+  c.n0 = nt * p.BN;
+  c.b0 = c.bidx / p.nb1;
+  c.b1 = c.bidx - c.b0 * p.nb1;
+  return c;
+}
+
+// kOcc = 2 (weight streaming): <= 96 registers, <= ~110 KB smem and only the TMEM columns it needs, so the CTA of the NEXT
+// GEMM in the stream (programmatic dependent launch) is resident and has its weight ring full before this one drains.
+template <int kOcc>
+__global__ void __launch_bounds__(GEMM_THREADS, kOcc)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * MAX_STAGES;    // [2]           MMA -> epilogue
   uint64_t* tempty = tfull + 2;               // [2]           epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  volatile int* s_last = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,52 +279,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], N_EPI_WARPS);
     }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmW);
-    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
-  const int units = p.n_tt * p.n_ft * p.ksplit * p.nbatch;
-  const uint32_t tx_bytes = A_STAGE_BYTES + p.BN * BK * 2;
+  const long long g0 = (long long)blockIdx.x * p.per;
+  const long long g1 = (g0 + p.per < p.total_kb) ? g0 + p.per : p.total_kb;
+  const uint32_t b_bytes = (uint32_t)p.BN * BK * 2;
+  const uint32_t tx_bytes = A_STAGE_BYTES + b_bytes;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int tt = u % p.n_tt;
-        const int ft = (u / p.n_tt) % p.n_ft;
-        const int ks = (u / (p.n_tt * p.n_ft)) % p.ksplit;
-        const int bidx = u / (p.n_tt * p.n_ft * p.ksplit);
-        const int b0 = bidx / p.nb1, b1 = bidx % p.nb1;
-        const int f0 = ft * BM, t0 = tt * p.BN;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+      // weight (A) tiles of the first ring fill do not depend on the previous kernel: issue them before the PDL wait
+      int pre = 0;
+      if (p.w_static) {
+        long long g = g0;
+        while (g < g1 && pre < p.num_stages) {
+          const Seg s = next_seg(g, g1, p.kb_total);
+          const TileCoord c = tile_coord(p, s.tile);
+          for (int kb = s.kb0; kb < s.kb1 && pre < p.num_stages; ++kb, ++pre) {
+            uint8_t* sa = smem + pre * p.stage_bytes;
+            mbar_arrive_expect_tx(&full[pre], tx_bytes);
+            tma_load_4d(sa, &tmA, &full[pre], kb * BK, c.m0, c.b1, c.b0);
+          }
+        }
+      }
+      pdl_wait();
+      int it = 0;
+      long long g = g0;
+      while (g < g1) {
+        const Seg s = next_seg(g, g1, p.kb_total);
+        const TileCoord c = tile_coord(p, s.tile);
+        for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
           uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], tx_bytes);
-          if (!p.w_mn) {
-            tma_load_4d(sa, &tmW, &full[stage], kb * BK, f0, b1, b0);
-          } else {
-            tma_load_4d(sa, &tmW, &full[stage], f0, kb * BK, b1, b0);
-            tma_load_4d(sa + 8192, &tmW, &full[stage], f0 + 64, kb * BK, b1, b0);
+          if (it >= pre) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], tx_bytes);
+            if (!p.a_mn) {
+              tma_load_4d(sa, &tmA, &full[stage], kb * BK, c.m0, c.b1, c.b0);
+            } else {
+              tma_load_4d(sa, &tmA, &full[stage], c.m0, kb * BK, c.b1, c.b0);
+              tma_load_4d(sa + 8192, &tmA, &full[stage], c.m0 + 64, kb * BK, c.b1, c.b0);
+            }
           }
-          if (!p.x_mn) {
-            tma_load_4d(sb, &tmX, &full[stage], kb * BK, t0, b1, b0);
+          if (!p.b_mn) {
+            tma_load_4d(sb, &tmB, &full[stage], kb * BK, c.n0, c.b1, c.b0);
           } else {
-            for (int i = 0; i < p.BN / 64; ++i) tma_load_4d(sb + i * 8192, &tmX, &full[stage], t0 + 64 * i, kb * BK, b1, b0);
+            for (int i = 0; i < p.BN / 64; ++i) tma_load_4d(sb + i * 8192, &tmB, &full[stage], c.n0 + 64 * i, kb * BK, c.b1, c.b0);
           }
           if (++stage == p.num_stages) {
             stage = 0;
@@ -159,16 +356,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      const uint32_t a_lbo = p.w_mn ? 8192 : 16, b_lbo = p.x_mn ? 8192 : 16;
-      const uint32_t a_kstep = p.w_mn ? 2048 : 32, b_kstep = p.x_mn ? 2048 : 32;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int ks = (u / (p.n_tt * p.n_ft)) % p.ksplit;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const uint32_t a_lbo = p.a_mn ? 8192 : 16, b_lbo = p.b_mn ? 8192 : 16;
+      const uint32_t a_kstep = p.a_mn ? 2048 : 32, b_kstep = p.b_mn ? 2048 : 32;
+      long long g = g0;
+      while (g < g1) {
+        const Seg s = next_seg(g, g1, p.kb_total);
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * ACC_STAGE_COLS;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
+        for (int kb = s.kb0; kb < s.kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
@@ -177,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t da = make_smem_desc(sa + kk * a_kstep, a_lbo, 1024);
             const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, 1024);
-            tc_mma_f16(d_tmem, da, db, p.idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            tc_mma_f16(d_tmem, da, db, p.idesc, (kb > s.kb0 || kk > 0) ? 1u : 0u);
           }
           tc_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
           if (++stage == p.num_stages) {
@@ -193,39 +389,96 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------ epilogue (warps 2..9) ------------------------------
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int hsel = (warp - 2) >> 2;     // which half of the column chunks this warp handles
+    const int epi_tid = threadIdx.x - 64;
+    const int lrow = q * 32 + lane;       // TMEM lane == row of the A tile
+    const bool swiglu = p.ep.act == MYR_ACT_SWIGLU;
     int as = 0;
     uint32_t aphase = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int tt = u % p.n_tt;
-      const int ft = (u / p.n_tt) % p.n_ft;
-      const int ks = (u / (p.n_tt * p.n_ft)) % p.ksplit;
-      const int bidx = u / (p.n_tt * p.n_ft * p.ksplit);
-      const long long boff = (long long)(bidx / p.nb1) * p.o_bs0 + (long long)(bidx % p.nb1) * p.o_bs1;
-      const int f = ft * BM + q * 32 + lane;
-      const int t0 = tt * p.BN;
+    pdl_wait();  // residual / output / workspace may still be in use by the previous kernel
+    long long g = g0;
+    while (g < g1) {
+      const Seg s = next_seg(g, g1, p.kb_total);
+      const TileCoord c = tile_coord(p, s.tile);
+      const long long boff = (long long)c.b0 * p.o_bs0 + (long long)c.b1 * p.o_bs1;
+      // which CTAs cover this tile
+      const long long tb = (long long)s.tile * p.kb_total;
+      const int first = (int)(tb / p.per), last = (int)((tb + p.kb_total - 1) / p.per);
+      const int n_seg = last - first + 1;
+      const int seg = (int)blockIdx.x - first;
+      const bool via_ws = n_seg > 1 || (swiglu && !p.row_mode);
+      const int nchunks = p.BN / 16;
+      float* ws = p.partial + ((size_t)s.tile * p.max_seg + seg) * ((size_t)p.BN * BM);
+
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STAGE_COLS;
-      const bool f_ok = f < p.F;
-      float bias_f = 0.f;
-      if (p.ksplit == 1 && p.ep.bias && f_ok) bias_f = __half2float(p.ep.bias[f]);
-      const int nchunks = min(p.BN, p.T - t0 + 15) / 16;  // chunks with at least one valid token
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c * 16, r);
-        tmem_ld_wait();
-        if (f_ok) {
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * p.acc_stride;
+
+      if (via_ws) {
+        for (int ch = hsel; ch < nchunks; ch += 2) {
+          uint32_t r[16];
+          tmem_ld16(taddr + ch * 16, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int t = t0 + c * 16 + j;
-            if (t < p.T) {
-              const float v = __uint_as_float(r[j]);
-              if (p.ksplit == 1)
-                epilogue_store(p.ep, v, bias_f, t, f, boff);
-              else
-                p.partial[((long long)ks * p.T + t) * p.F + f] = v;
+          for (int j = 0; j < 16; ++j) ws[(size_t)(ch * 16 + j) * BM + lrow] = __uint_as_float(r[j]);
+        }
+      } else if (p.row_mode) {
+        const long long t = (long long)c.m0 + lrow;
+        const bool t_ok = t < p.T;
+        const long long obase = boff + (t_ok ? out_row_offset(p.ep, t) : 0);
+        if (!swiglu) {
+          for (int ch = hsel; ch < nchunks; ch += 2) {
+            const int f0 = c.n0 + ch * 16;
+            if (f0 >= p.F) break;
+            uint32_t r[16];
+            tmem_ld16(taddr + ch * 16, r);
+            tmem_ld_wait();
+            if (t_ok) {
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+              epi_row16(p.ep, v, t, f0, p.F, obase);
+            }
+          }
+        } else {
+          // weight rows are interleaved in blocks of 64: [gate 0..63 | up 0..63 | gate 64..127 | ...]
+          const int units = p.BN / 32;  // 16-wide gate chunks in this tile
+          for (int u = hsel; u < units; u += 2) {
+            const int blk = u >> 2, cg = u & 3;
+            const int gcol = blk * 128 + cg * 16;
+            if (c.n0 + gcol >= p.F) break;
+            uint32_t rg[16], ru[16];
+            tmem_ld16(taddr + gcol, rg);
+            tmem_ld16(taddr + gcol + 64, ru);
+            tmem_ld_wait();
+            if (t_ok) {
+              float gv[16], uv[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                gv[j] = __uint_as_float(rg[j]);
+                uv[j] = __uint_as_float(ru[j]);
+              }
+              epi_row16_swiglu(p.ep, gv, uv, (c.n0 >> 1) + blk * 64 + cg * 16, p.F >> 1, obase);
+            }
+          }
+        }
+      } else {
+        // lanes = features, single segment: straight from TMEM
+        const int f = c.m0 + lrow;
+        const bool f_ok = f < p.F;
+        const float bias_f = (p.ep.bias && f_ok) ? __half2float(p.ep.bias[f]) : 0.f;
+        for (int ch = hsel; ch < nchunks; ch += 2) {
+          if (c.n0 + ch * 16 >= p.T) break;
+          uint32_t r[16];
+          tmem_ld16(taddr + ch * 16, r);
+          tmem_ld_wait();
+          if (f_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int t = c.n0 + ch * 16 + j;
+              if (t < p.T) epi_store_scalar(p.ep, epi_transform(p.ep, __uint_as_float(r[j]), bias_f, f), t, f, boff);
             }
           }
         }
@@ -237,90 +490,198 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         as = 0;
         aphase ^= 1;
       }
+
+      if (via_ws) {
+        // publish the partial, elect the finisher (last CTA to arrive at this tile)
+        __threadfence();
+        epi_bar_sync();
+        if (epi_tid == 0) {
+          int lastf = 1;
+          if (n_seg > 1) {
+            const int old = atomicAdd(&p.counters[s.tile], 1);
+            lastf = (old == n_seg - 1);
+            if (lastf) p.counters[s.tile] = 0;  // every segment has arrived: leave the counter clean for the next launch
+          }
+          *s_last = lastf;
+        }
+        epi_bar_sync();
+        const int lastf = *s_last;
+        if (lastf) {
+          __threadfence();
+          const float* w0 = p.partial + (size_t)s.tile * p.max_seg * ((size_t)p.BN * BM);
+          const size_t seg_stride = (size_t)p.BN * BM;
+          if (p.row_mode) {
+            const long long t = (long long)c.m0 + lrow;
+            if (t < p.T) {
+              const long long obase = boff + out_row_offset(p.ep, t);
+              if (!swiglu) {
+                for (int ch = hsel; ch < nchunks; ch += 2) {
+                  const int f0 = c.n0 + ch * 16;
+                  if (f0 >= p.F) break;
+                  float v[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    float a = 0.f;
+                    for (int sg = 0; sg < n_seg; ++sg) a += __ldcg(w0 + sg * seg_stride + (size_t)(ch * 16 + j) * BM + lrow);
+                    v[j] = a;
+                  }
+                  epi_row16(p.ep, v, t, f0, p.F, obase);
+                }
+              } else {
+                const int units = p.BN / 32;
+                for (int u = hsel; u < units; u += 2) {
+                  const int blk = u >> 2, cg = u & 3;
+                  const int gcol = blk * 128 + cg * 16;
+                  if (c.n0 + gcol >= p.F) break;
+                  float gv[16], uv[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    float a = 0.f, b = 0.f;
+                    for (int sg = 0; sg < n_seg; ++sg) {
+                      a += __ldcg(w0 + sg * seg_stride + (size_t)(gcol + j) * BM + lrow);
+                      b += __ldcg(w0 + sg * seg_stride + (size_t)(gcol + 64 + j) * BM + lrow);
+                    }
+                    gv[j] = a;
+                    uv[j] = b;
+                  }
+                  epi_row16_swiglu(p.ep, gv, uv, (c.n0 >> 1) + blk * 64 + cg * 16, p.F >> 1, obase);
+                }
+              }
+            }
+          } else if (!swiglu) {
+            const int f = c.m0 + lrow;
+            if (f < p.F) {
+              const float bias_f = p.ep.bias ? __half2float(p.ep.bias[f]) : 0.f;
+              for (int col = hsel; col < p.BN; col += 2) {
+                const int t = c.n0 + col;
+                if (t >= p.T) break;
+                float a = 0.f;
+                for (int sg = 0; sg < n_seg; ++sg) a += __ldcg(w0 + sg * seg_stride + (size_t)col * BM + lrow);
+                epi_store_scalar(p.ep, epi_transform(p.ep, a, bias_f, f), t, f, boff);
+              }
+            }
+          } else if (lrow < 64) {
+            // lanes = features with SwiGLU: lane l holds gate row l, lane l + 64 the matching up row
+            const int i = (c.m0 >> 1) + lrow;
+            if (i < (p.F >> 1)) {
+              for (int col = hsel; col < p.BN; col += 2) {
+                const int t = c.n0 + col;
+                if (t >= p.T) break;
+                float a = 0.f, b = 0.f;
+                for (int sg = 0; sg < n_seg; ++sg) {
+                  a += __ldcg(w0 + sg * seg_stride + (size_t)col * BM + lrow);
+                  b += __ldcg(w0 + sg * seg_stride + (size_t)col * BM + lrow + 64);
+                }
+                reinterpret_cast<__half*>(p.ep.out)[boff + out_row_offset(p.ep, t) + i] = __float2half_rn(swiglu_pair(a, b));
+              }
+            }
+          }
+        }
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-// split-K: sum fp32 partials in fixed order (deterministic) and apply the epilogue.
-__global__ void gemm_splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, int T, int F, Epilogue ep) {
-  const long long n = (long long)T * F;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(i % F);
-    const long long t = i / F;
-    float v = 0.f;
-    for (int s = 0; s < ksplit; ++s) v += partial[(long long)s * n + i];
-    const float b = ep.bias ? __half2float(ep.bias[f]) : 0.f;
-    epilogue_store(ep, v, b, t, f);
-  }
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// host side: tile-shape heuristics
+// host side: operand arrangement, tile shape and range length
 // ---------------------------------------------------------------------------------------------------
 struct Plan {
-  int BN, n_tt, n_ft, ksplit, kb_total, kb_per_split, num_stages, stage_bytes;
+  int row_mode, BN, n_mt, n_nt, kb_total, per, grid, max_seg, num_stages, stage_bytes;
+  long long total_kb;
+  int n_tiles;
 };
 
-static Plan make_plan(int T, int F, int K, int x_mn, int bn_hint, int ksplit_hint) {
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static Plan make_plan(const myr_gemm_args* a, int nbatch, bool allow_split, size_t ws_floats) {
   Plan pl;
   const int sms = sm_count();
-  pl.n_ft = ceil_div(F, BM);
+  const int T = a->T, F = a->F, K = a->K;
+  const bool swiglu = a->act == MYR_ACT_SWIGLU;
   pl.kb_total = ceil_div(K, BK);
-  const int gran = x_mn ? 64 : 16;
-  int best_bn = 0;
-  if (bn_hint > 0) {
-    best_bn = bn_hint;
-  } else {
-    const int t_pad = ceil_div(T, gran) * gran;
-    if (t_pad <= 256) {
-      best_bn = t_pad;
+  pl.row_mode = (T > 64) ? 1 : 0;
+  int gran;
+  if (pl.row_mode) {
+    gran = swiglu ? 128 : (a->w_mn_major ? 64 : 16);
+    pl.n_mt = ceil_div(T, BM);
+    int best_bn = 0;
+    if (a->bn_hint > 0) {
+      best_bn = round_up(a->bn_hint, gran);
+      if (best_bn > 256) best_bn = 256;
     } else {
-      // cost model (cycles per k-step of 16): MMA = BN/2, smem operand reads = 32 + BN/4; rounds of persistent CTAs.
+      // cost (cycles per 16-wide k-step): MMA = BN/2, smem operand reads = 32 + BN/4; x rounds of persistent CTAs
       double best = 1e30;
-      for (int bn = 256; bn >= 64; bn -= gran) {
-        const int n_tt = ceil_div(T, bn);
-        const long long tiles = (long long)n_tt * pl.n_ft;
+      const int f_cap = round_up(F, gran);
+      for (int bn = 256; bn >= (gran > 32 ? gran : 32); bn -= gran) {
+        if (bn > f_cap && bn != gran) continue;
+        const long long tiles = (long long)pl.n_mt * ceil_div(F, bn) * nbatch;
         const long long rounds = (tiles + sms - 1) / sms;
         const double per = (bn / 2.0 > 32 + bn / 4.0) ? bn / 2.0 : 32 + bn / 4.0;
-        const double cost = rounds * (per + 6.0);
+        const double cost = rounds * (pl.kb_total * 4 * per + 400.0 + 3.0 * bn);
         if (cost < best - 1e-9) {
           best = cost;
           best_bn = bn;
         }
       }
+      if (best_bn == 0) best_bn = gran > 32 ? gran : 32;
     }
+    pl.BN = best_bn;
+    pl.n_nt = ceil_div(F, pl.BN);
+  } else {
+    gran = a->x_mn_major ? 64 : 16;
+    pl.BN = round_up(T, gran);
+    if (a->bn_hint > 0 && round_up(a->bn_hint, gran) < pl.BN) pl.BN = round_up(a->bn_hint, gran);
+    pl.n_mt = ceil_div(F, BM);
+    pl.n_nt = ceil_div(T, pl.BN);
   }
-  pl.BN = best_bn;
-  pl.n_tt = ceil_div(T, pl.BN);
-  const int tiles = pl.n_tt * pl.n_ft;
-  int ks = 1;
-  if (ksplit_hint > 0) {
-    ks = ksplit_hint;
-  } else if (tiles < sms && pl.kb_total >= 16) {
-    // weight-streaming regime: spread k-blocks over idle SMs; pick the split with the best wave efficiency.
-    double best = 0;
-    for (int cand = 1; cand <= 16; ++cand) {
-      const int per = ceil_div(pl.kb_total, cand);
-      if (per < 8 && cand > 1) break;
-      const int eff_ks = ceil_div(pl.kb_total, per);
-      const long long units = (long long)tiles * eff_ks;
-      const long long rounds = (units + sms - 1) / sms;
-      const double eff = (double)units / (double)(rounds * sms);
-      if (eff > best + 0.02) {
-        best = eff;
-        ks = eff_ks;
-      }
-    }
-  }
-  pl.kb_per_split = ceil_div(pl.kb_total, ks);
-  pl.ksplit = ceil_div(pl.kb_total, pl.kb_per_split);
+  pl.n_tiles = pl.n_mt * pl.n_nt * nbatch;
+  pl.total_kb = (long long)pl.n_tiles * pl.kb_total;
   pl.stage_bytes = A_STAGE_BYTES + pl.BN * BK * 2;
-  int st = SMEM_TILE_BUDGET / pl.stage_bytes;
+  int st = (pl.row_mode ? SMEM_TILE_BUDGET : SMEM_TILE_BUDGET_OCC2) / pl.stage_bytes;
   pl.num_stages = st > MAX_STAGES ? MAX_STAGES : st;
+
+  // data-parallel default: whole tiles per CTA
+  const int tiles_per_cta = ceil_div(pl.n_tiles, sms);
+  pl.per = tiles_per_cta * pl.kb_total;
+  pl.grid = ceil_div(pl.n_tiles, tiles_per_cta);
+  pl.max_seg = 1;
+  bool want_split = false;
+  int per = pl.per;
+  if (a->ksplit_hint > 1) {
+    per = ceil_div(pl.kb_total, a->ksplit_hint);
+    want_split = true;
+  } else if (a->ksplit_hint == 0 && allow_split && pl.total_kb >= 2LL * sms) {
+    const double dp_eff = (double)pl.n_tiles / ((double)tiles_per_cta * sms);
+    const int sk_per = (int)((pl.total_kb + sms - 1) / sms);
+    if (!pl.row_mode) {
+      // weight streaming: balance bytes across all SMs unless the data-parallel schedule is already balanced
+      want_split = dp_eff < 0.95 && sk_per >= 2;
+    } else {
+      // tensor-bound: partial tiles cost L2 traffic, so split only when few tiles would leave most SMs idle
+      want_split = dp_eff < 0.7 && pl.n_tiles < sms && pl.kb_total >= 16 && sk_per >= 4;
+    }
+    per = sk_per;
+  }
+  if (want_split && nbatch == 1) {
+    const int max_seg = (pl.kb_total + per - 1) / per + 1;
+    const size_t need = (size_t)pl.n_tiles * max_seg * pl.BN * BM;
+    if (pl.n_tiles <= MAX_COUNTERS && need <= ws_floats) {
+      pl.per = per;
+      pl.grid = (int)((pl.total_kb + per - 1) / per);
+      pl.max_seg = max_seg;
+    } else if (a->ksplit_hint > 1) {
+      pl.grid = -1;  // explicit request that cannot be honoured
+    }
+  }
+  if (!pl.row_mode && swiglu && pl.max_seg == 1) {
+    // lanes = features SwiGLU always finishes through the workspace (gate / up rows sit on different lanes)
+    const size_t need = (size_t)pl.n_tiles * pl.BN * BM;
+    if (need > ws_floats) pl.grid = -1;
+  }
   return pl;
 }
 
@@ -330,8 +691,9 @@ using namespace myr;
 
 extern "C" size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K) {
   (void)K;
-  // upper bound: 16-way split-K is only chosen when tiles < #SMs, i.e. small T*F
-  return (size_t)16 * (size_t)T * (size_t)F * sizeof(float);
+  // counters + partial tiles: a split tile keeps at most ceil(kb / per) + 1 <= 4 partials in the shapes the heuristics pick
+  const size_t tiles = (size_t)ceil_div(T > 64 ? T : F, BM) * (size_t)ceil_div(T > 64 ? F : T, T > 64 ? 256 : 64);
+  return COUNTER_BYTES + tiles * 4 * 256 * BM * sizeof(float);
 }
 
 extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
@@ -348,58 +710,87 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   MYR_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
                 "gemm: x/w must be 16-byte aligned");
   MYR_CHECK_ARG(a->out != nullptr && a->x != nullptr && a->w != nullptr, "gemm: null pointer");
-  MYR_CHECK_ARG(a->bn_hint == 0 || (a->bn_hint % 16 == 0 && a->bn_hint >= 16 && a->bn_hint <= 256),
-                "gemm: bn_hint=%d must be a multiple of 16 in [16,256]", a->bn_hint);
-  MYR_CHECK_ARG(!a->x_mn_major || a->bn_hint % 64 == 0, "gemm: MN-major x needs bn_hint multiple of 64");
+  MYR_CHECK_ARG(a->bn_hint >= 0 && a->bn_hint <= 256, "gemm: bn_hint=%d must be in [0,256]", a->bn_hint);
+  const bool swiglu = a->act == MYR_ACT_SWIGLU;
+  if (swiglu) {
+    MYR_CHECK_ARG(a->F % 128 == 0 && a->bias == nullptr && a->res == nullptr && a->out_dtype == MYR_F16 && nbatch == 1 &&
+                      !a->w_mn_major && a->scale_cols == 0,
+                  "gemm: SwiGLU epilogue needs F %% 128 == 0 (64-row interleaved gate/up), fp16 out, no bias/residual");
+  }
+  MYR_CHECK_ARG(a->T <= 64 || !a->x_mn_major || true, "gemm: unreachable");
 
-  Plan pl = make_plan(a->T, a->F, a->K, a->x_mn_major, a->bn_hint, nbatch > 1 ? 1 : a->ksplit_hint);
-  if (pl.ksplit > 1) {
-    const size_t need = (size_t)pl.ksplit * a->T * a->F * sizeof(float);
-    if (a->workspace == nullptr || a->workspace_bytes < need) {
-      if (a->ksplit_hint > 0) {
-        set_error("gemm: split-K=%d needs %zu workspace bytes, got %zu", pl.ksplit, need, a->workspace_bytes);
-        return MYR_ERR_WORKSPACE;
-      }
-      pl = make_plan(a->T, a->F, a->K, a->x_mn_major, a->bn_hint, 1);  // silently valid: no split, same result order
-    }
+  size_t ws_floats = 0;
+  int* counters = nullptr;
+  float* partial = nullptr;
+  if (a->workspace != nullptr && a->workspace_bytes > COUNTER_BYTES && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0) {
+    counters = reinterpret_cast<int*>(a->workspace);
+    partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + COUNTER_BYTES);
+    ws_floats = (a->workspace_bytes - COUNTER_BYTES) / sizeof(float);
+  }
+  Plan pl = make_plan(a, nbatch, true, ws_floats);
+  if (pl.grid < 0) {
+    set_error("gemm: split-K / SwiGLU fix-up needs a larger workspace (got %zu bytes)", a->workspace_bytes);
+    return MYR_ERR_WORKSPACE;
   }
 
-  CUtensorMap tmW, tmX;
+  // operand roles: A = the 128-row side, B = the BN side
+  const void* pa = pl.row_mode ? a->x : a->w;
+  const void* pb = pl.row_mode ? a->w : a->x;
+  const int64_t lda = pl.row_mode ? a->ldx : a->ldw, ldb = pl.row_mode ? a->ldw : a->ldx;
+  const int a_mn = pl.row_mode ? a->x_mn_major : a->w_mn_major, b_mn = pl.row_mode ? a->w_mn_major : a->x_mn_major;
+  const int rows_a = pl.row_mode ? a->T : a->F, rows_b = pl.row_mode ? a->F : a->T;
+  const int64_t a_bs0 = pl.row_mode ? a->x_bs0 : a->w_bs0, a_bs1 = pl.row_mode ? a->x_bs1 : a->w_bs1;
+  const int64_t b_bs0 = pl.row_mode ? a->w_bs0 : a->x_bs0, b_bs1 = pl.row_mode ? a->w_bs1 : a->x_bs1;
+  MYR_CHECK_ARG(!b_mn || pl.BN % 64 == 0, "gemm: MN-major operand on the N side needs a tile multiple of 64 (BN=%d)", pl.BN);
+
+  CUtensorMap tmA, tmB;
   {
     uint64_t dims[4], strides[3];
     uint32_t box[4];
     dims[2] = (uint64_t)nb1; dims[3] = (uint64_t)nb0; box[2] = 1; box[3] = 1;
-    if (!a->w_mn_major) {
-      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)a->F; box[0] = BK; box[1] = BM;
+    if (!a_mn) {
+      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)rows_a; box[0] = BK; box[1] = BM;
     } else {
-      dims[0] = (uint64_t)a->F; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
+      dims[0] = (uint64_t)rows_a; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
     }
-    strides[0] = (uint64_t)a->ldw * 2;
-    strides[1] = nb1 > 1 ? (uint64_t)a->w_bs1 * 2 : strides[0] * dims[1];
-    strides[2] = nb0 > 1 ? (uint64_t)a->w_bs0 * 2 : strides[1] * dims[2];
-    int rc = make_tmap_f16(&tmW, a->w, 4, dims, strides, box);
+    strides[0] = (uint64_t)lda * 2;
+    strides[1] = nb1 > 1 ? (uint64_t)a_bs1 * 2 : strides[0] * dims[1];
+    strides[2] = nb0 > 1 ? (uint64_t)a_bs0 * 2 : strides[1] * dims[2];
+    int rc = make_tmap_f16(&tmA, pa, 4, dims, strides, box);
     if (rc) return rc;
-    if (!a->x_mn_major) {
-      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)a->T; box[0] = BK; box[1] = (uint32_t)pl.BN;
+    if (!b_mn) {
+      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)rows_b; box[0] = BK; box[1] = (uint32_t)pl.BN;
     } else {
-      dims[0] = (uint64_t)a->T; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
+      dims[0] = (uint64_t)rows_b; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
     }
-    strides[0] = (uint64_t)a->ldx * 2;
-    strides[1] = nb1 > 1 ? (uint64_t)a->x_bs1 * 2 : strides[0] * dims[1];
-    strides[2] = nb0 > 1 ? (uint64_t)a->x_bs0 * 2 : strides[1] * dims[2];
-    rc = make_tmap_f16(&tmX, a->x, 4, dims, strides, box);
+    strides[0] = (uint64_t)ldb * 2;
+    strides[1] = nb1 > 1 ? (uint64_t)b_bs1 * 2 : strides[0] * dims[1];
+    strides[2] = nb0 > 1 ? (uint64_t)b_bs0 * 2 : strides[1] * dims[2];
+    rc = make_tmap_f16(&tmB, pb, 4, dims, strides, box);
     if (rc) return rc;
   }
 
   GemmKernelParams p;
   p.T = a->T; p.F = a->F; p.K = a->K;
-  p.BN = pl.BN; p.n_tt = pl.n_tt; p.n_ft = pl.n_ft; p.ksplit = pl.ksplit;
-  p.kb_total = pl.kb_total; p.kb_per_split = pl.kb_per_split;
+  p.row_mode = pl.row_mode;
+  p.BN = pl.BN; p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.kb_total = pl.kb_total;
+  p.total_kb = pl.total_kb; p.per = pl.per; p.max_seg = pl.max_seg;
   p.num_stages = pl.num_stages; p.stage_bytes = pl.stage_bytes;
-  p.x_mn = a->x_mn_major; p.w_mn = a->w_mn_major;
-  p.idesc = make_idesc_f16(BM, pl.BN, a->w_mn_major, a->x_mn_major);
-  p.partial = reinterpret_cast<float*>(a->workspace);
+  p.a_mn = a_mn; p.b_mn = b_mn;
+  p.idesc = make_idesc_f16(BM, pl.BN, a_mn, b_mn);
+  p.partial = partial; p.counters = counters;
   p.nb1 = nb1; p.nbatch = nbatch; p.o_bs0 = a->o_bs0; p.o_bs1 = a->o_bs1;
+  // weights may be prefetched ahead of the dependency only when they are the K-major A operand and the caller says so
+  p.w_static = (a->w_static && !pl.row_mode && !a_mn) ? 1 : 0;
+  if (pl.row_mode) {
+    p.tmem_cols = TMEM_COLS;
+    p.acc_stride = ACC_STAGE_COLS;
+  } else {
+    int cols = 32;
+    while (cols < 2 * pl.BN) cols <<= 1;
+    p.tmem_cols = cols;
+    p.acc_stride = cols / 2;
+  }
   p.ep.bias = reinterpret_cast<const __half*>(a->bias);
   p.ep.act = a->act; p.ep.round_acc = a->round_acc;
   p.ep.scale_cols = a->scale_cols; p.ep.scale = a->scale;
@@ -407,23 +798,28 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   p.ep.out = a->out; p.ep.out_dtype = a->out_dtype; p.ep.ldo = a->ldo;
   p.ep.group_rows = a->out_group_rows; p.ep.group_stride = a->out_group_stride;
   p.ep.alpha = a->alpha_set ? a->alpha : 1.0f;
+  {
+    const int oq = a->out_dtype == MYR_F32 ? 4 : 8, rq = a->res_dtype == MYR_F32 ? 4 : 8;
+    bool v = (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && a->ldo % oq == 0 && a->out_group_stride % oq == 0 &&
+             a->o_bs0 % oq == 0 && a->o_bs1 % oq == 0;
+    if (a->res) v = v && (reinterpret_cast<uintptr_t>(a->res) & 15) == 0 && a->ldr % rq == 0;
+    if (a->bias) v = v && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0;
+    p.ep.vec = v ? 1 : 0;
+  }
 
   const size_t smem_bytes = (size_t)pl.num_stages * pl.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    MYR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr_set = true;
   }
-  const int units = pl.n_tt * pl.n_ft * pl.ksplit * nbatch;
-  const int grid = units < sm_count() ? units : sm_count();
-  gemm_tc_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tmW, tmX, p);
+  if (pl.row_mode)
+    MYR_CHECK_CUDA(launch_kernel(gemm_tc_kernel<1>, dim3((unsigned)pl.grid), dim3(GEMM_THREADS), smem_bytes, stream, a->pdl != 0,
+                                 tmA, tmB, p));
+  else
+    MYR_CHECK_CUDA(launch_kernel(gemm_tc_kernel<2>, dim3((unsigned)pl.grid), dim3(GEMM_THREADS), smem_bytes, stream, a->pdl != 0,
+                                 tmA, tmB, p));
   MYR_CHECK_LAUNCH();
-  if (pl.ksplit > 1) {
-    const long long n = (long long)a->T * a->F;
-    int rgrid = (int)((n + 255) / 256);
-    if (rgrid > sm_count() * 8) rgrid = sm_count() * 8;
-    gemm_splitk_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.partial, pl.ksplit, a->T, a->F, p.ep);
-    MYR_CHECK_LAUNCH();
-  }
   return MYR_OK;
 }

@@ -12,6 +12,8 @@ namespace myr {
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, long long ld, int V,
                                                       const int* __restrict__ state, int min_new, int eos,
                                                       int* __restrict__ raw) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float sv[32];
   __shared__ int si[32];
   const int b = blockIdx.x;
@@ -63,7 +65,10 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
 //   [4+4B .. 4+4B+B*max_new) tokens (row-major [B, max_new])
 __global__ void greedy_update_kernel(int* __restrict__ state, const int* __restrict__ raw, int B, int max_new, int eos,
                                      const int* __restrict__ stops, int n_stops, int stop_max_len) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (state[1]) return;  // already done: decode steps replayed past the stop (the host polls every few steps) change nothing
   const int step = state[0];
   int* unfinished = state + 4;
   int* cur = state + 4 + B;
@@ -104,13 +109,13 @@ extern "C" int myr_greedy_step(const void* logits, int64_t ld_logits, int32_t B,
                                int32_t n_stops, int32_t stop_max_len, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MYR_CHECK_ARG(logits && state && scratch && B > 0 && V > 0 && max_new_tokens > 0, "greedy_step: bad arguments");
-  argmax_kernel<<<B, 1024, 0, stream>>>(reinterpret_cast<const float*>(logits), ld_logits, V,
-                                        reinterpret_cast<const int*>(state), min_new_tokens, eos,
-                                        reinterpret_cast<int*>(scratch));
+  MYR_CHECK_CUDA(launch_kernel(argmax_kernel, dim3(B), dim3(1024), 0, stream, true, reinterpret_cast<const float*>(logits),
+                               (long long)ld_logits, V, reinterpret_cast<const int*>(state), min_new_tokens, eos,
+                               reinterpret_cast<int*>(scratch)));
   MYR_CHECK_LAUNCH();
-  greedy_update_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<int*>(state), reinterpret_cast<const int*>(scratch), B,
-                                             max_new_tokens, eos, reinterpret_cast<const int*>(stop_seqs), n_stops,
-                                             stop_max_len);
+  MYR_CHECK_CUDA(launch_kernel(greedy_update_kernel, dim3(1), dim3(32), 0, stream, true, reinterpret_cast<int*>(state),
+                               reinterpret_cast<const int*>(scratch), B, max_new_tokens, eos,
+                               reinterpret_cast<const int*>(stop_seqs), n_stops, stop_max_len));
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }

@@ -55,6 +55,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor is still running; it must execute pdl_wait() before touching anything the predecessor writes (or
+// reads, if this kernel overwrites it). pdl_launch_dependents() lets the NEXT kernel's CTAs start early.
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // generic-proxy writes (st.shared) -> visible to async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -66,6 +66,8 @@ struct NormParams {
 // fp32 statistics, two-pass variance on register-resident data. Optional fused LoraAdaptorV2 (networks.py:81-93).
 __global__ void __launch_bounds__(NORM_THREADS) norm_kernel(const NormParams p) {
   __shared__ float red[(NORM_THREADS / 32) * 4];
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x;
   const int nvec = p.D >> 2;
   const char* xrow = reinterpret_cast<const char*>(p.x) + (size_t)row * p.ldx * (p.x_dtype == MYR_F32 ? 4 : 2);
@@ -165,6 +167,10 @@ struct RopeParams {
   __half* kcache; __half* vcache; long long c_ts, c_bs;  // cache element strides (token, batch)
   const int* cache_off;  // device scalar: first cache slot for s = 0 (null -> cache_off_host)
   int cache_off_host;
+  // peft LoRA on q_proj / v_proj (myriad.py:171-178): xa = x A^T sits in columns [3*H*dh, 3*H*dh + 2r) of the qkv row
+  // (A rows are appended to the fused qkv weight); q += scale * B_q xa[:r], v += scale * B_v xa[r:], before the rotation.
+  const __half* lora_bq; const __half* lora_bv;  // [H*dh, r] fp16, r == 8
+  int lora_r; float lora_scale;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -184,7 +190,22 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
+// y[k] += scale * sum_r B[(row0 + k), r] * xa[r] for 8 consecutive output features (r == 8: one 16-byte row of B each)
+__device__ __forceinline__ void lora_add8(float (&y)[8], const __half* __restrict__ b, int row0, const float (&xa)[8], float scale) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float w[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(b + (size_t)(row0 + k) * 8)), w);
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a = fmaf(w[r], xa[r], a);
+    y[k] = fmaf(scale, a, y[k]);
+  }
+}
+
 __global__ void rope_cache_kernel(const RopeParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int half = p.dh >> 1, hv = half >> 3;  // 8-wide vectors per half
   const long long total = (long long)p.B * p.S * p.H * hv;
   const int off = p.cache_off ? *p.cache_off : p.cache_off_host;
@@ -212,6 +233,12 @@ __global__ void rope_cache_kernel(const RopeParams p) {
       float x1[8], x2[8], o1[8], o2[8];
       unpack8(*reinterpret_cast<const uint4*>(src + vi * 8), x1);
       unpack8(*reinterpret_cast<const uint4*>(src + half + vi * 8), x2);
+      if (which == 0 && p.lora_r) {
+        float xa[8];
+        unpack8(*reinterpret_cast<const uint4*>(row + 3 * HD), xa);
+        lora_add8(x1, p.lora_bq, h * p.dh + vi * 8, xa, p.lora_scale);
+        lora_add8(x2, p.lora_bq, h * p.dh + half + vi * 8, xa, p.lora_scale);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         o1[k] = x1[k] * c[k] - x2[k] * sn[k];
@@ -222,14 +249,27 @@ __global__ void rope_cache_kernel(const RopeParams p) {
       *reinterpret_cast<uint4*>(dst + half + vi * 8) = pack8(o2);
     }
     const __half* vsrc = row + 2 * HD + h * p.dh;
-    *reinterpret_cast<uint4*>(vdst + vi * 8) = *reinterpret_cast<const uint4*>(vsrc + vi * 8);
-    *reinterpret_cast<uint4*>(vdst + half + vi * 8) = *reinterpret_cast<const uint4*>(vsrc + half + vi * 8);
+    if (!p.lora_r) {
+      *reinterpret_cast<uint4*>(vdst + vi * 8) = *reinterpret_cast<const uint4*>(vsrc + vi * 8);
+      *reinterpret_cast<uint4*>(vdst + half + vi * 8) = *reinterpret_cast<const uint4*>(vsrc + half + vi * 8);
+    } else {
+      float xa[8], v1[8], v2[8];
+      unpack8(*reinterpret_cast<const uint4*>(row + 3 * HD + 8), xa);
+      unpack8(*reinterpret_cast<const uint4*>(vsrc + vi * 8), v1);
+      unpack8(*reinterpret_cast<const uint4*>(vsrc + half + vi * 8), v2);
+      lora_add8(v1, p.lora_bv, h * p.dh + vi * 8, xa, p.lora_scale);
+      lora_add8(v2, p.lora_bv, h * p.dh + half + vi * 8, xa, p.lora_scale);
+      *reinterpret_cast<uint4*>(vdst + vi * 8) = pack8(v1);
+      *reinterpret_cast<uint4*>(vdst + half + vi * 8) = pack8(v2);
+    }
   }
 }
 
 // SwiGLU (modeling_llama.py:139-140): out[t, i] = silu(gu[t, i]) * gu[t, I + i]
 __global__ void swiglu_kernel(const __half* __restrict__ gu, long long ldg, __half* __restrict__ out, long long ldo, int T,
                               int I) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int iv = I >> 3;
   const long long total = (long long)T * iv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -247,6 +287,8 @@ __global__ void swiglu_kernel(const __half* __restrict__ gu, long long ldg, __ha
 // Embedding gather (myriad.py:308-311): out[r, :] = table[ids[r], :]  (fp16 table -> fp32 or fp16 rows)
 __global__ void embed_kernel(const __half* __restrict__ table, int D, const long long* __restrict__ ids64,
                              const int* __restrict__ ids32, int n, void* out, int out_dtype, long long ldo) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int dv = D >> 3;
   const long long total = (long long)n * dv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -335,7 +377,7 @@ extern "C" int myr_norm_fwd(const myr_norm_args* a, void* stream_) {
   p.out32 = reinterpret_cast<float*>(a->out32); p.ld32 = a->ld32;
   p.pre32 = reinterpret_cast<float*>(a->pre32); p.ldpre = a->ldpre;
   p.stats = reinterpret_cast<float*>(a->stats);
-  norm_kernel<<<a->rows, NORM_THREADS, 0, stream>>>(p);
+  MYR_CHECK_CUDA(launch_kernel(norm_kernel, dim3(a->rows), dim3(NORM_THREADS), 0, stream, true, p));
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }
@@ -353,8 +395,13 @@ extern "C" int myr_rope_cache(const myr_rope_args* a, void* stream_) {
   p.kcache = reinterpret_cast<__half*>(a->kcache); p.vcache = reinterpret_cast<__half*>(a->vcache);
   p.c_ts = a->cache_token_stride; p.c_bs = a->cache_batch_stride;
   p.cache_off = reinterpret_cast<const int*>(a->cache_off_dev); p.cache_off_host = a->cache_off;
+  p.lora_bq = reinterpret_cast<const __half*>(a->lora_bq); p.lora_bv = reinterpret_cast<const __half*>(a->lora_bv);
+  p.lora_r = (a->lora_bq && a->lora_bv) ? a->lora_r : 0; p.lora_scale = a->lora_scale;
+  MYR_CHECK_ARG(p.lora_r == 0 || p.lora_r == 8, "rope: fused LoRA supports rank 8 only (got %d)", p.lora_r);
+  MYR_CHECK_ARG(p.lora_r == 0 || ((reinterpret_cast<uintptr_t>(a->lora_bq) | reinterpret_cast<uintptr_t>(a->lora_bv)) & 15) == 0,
+                "rope: LoRA B matrices must be 16-byte aligned");
   const long long total = (long long)a->B * a->S * a->H * (a->dh / 16);
-  rope_cache_kernel<<<ew_grid(total, 256), 256, 0, stream>>>(p);
+  MYR_CHECK_CUDA(launch_kernel(rope_cache_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, stream, true, p));
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }
@@ -363,8 +410,9 @@ extern "C" int myr_swiglu(const void* gate_up, int64_t ld_gu, void* out, int64_t
                           void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MYR_CHECK_ARG(gate_up && out && T > 0 && I > 0 && I % 8 == 0 && ld_gu % 8 == 0 && ld_out % 8 == 0, "swiglu: bad arguments");
-  swiglu_kernel<<<ew_grid((long long)T * (I / 8), 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(gate_up), ld_gu,
-                                                                         reinterpret_cast<__half*>(out), ld_out, T, I);
+  MYR_CHECK_CUDA(launch_kernel(swiglu_kernel, dim3(ew_grid((long long)T * (I / 8), 256)), dim3(256), 0, stream, true,
+                               reinterpret_cast<const __half*>(gate_up), (long long)ld_gu, reinterpret_cast<__half*>(out),
+                               (long long)ld_out, T, I));
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }
@@ -373,9 +421,11 @@ extern "C" int myr_embed(const void* table, int32_t D, const void* ids, int32_t 
                          int32_t out_dtype, int64_t ld_out, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MYR_CHECK_ARG(table && ids && out && n > 0 && D % 8 == 0 && ld_out % 8 == 0, "embed: bad arguments");
-  embed_kernel<<<ew_grid((long long)n * (D / 8), 256), 256, 0, stream>>>(
-      reinterpret_cast<const __half*>(table), D, ids_are_int64 ? reinterpret_cast<const long long*>(ids) : nullptr,
-      ids_are_int64 ? nullptr : reinterpret_cast<const int*>(ids), n, out, out_dtype, ld_out);
+  MYR_CHECK_CUDA(launch_kernel(embed_kernel, dim3(ew_grid((long long)n * (D / 8), 256)), dim3(256), 0, stream, true,
+                               reinterpret_cast<const __half*>(table), D,
+                               ids_are_int64 ? reinterpret_cast<const long long*>(ids) : (const long long*)nullptr,
+                               ids_are_int64 ? (const int*)nullptr : reinterpret_cast<const int*>(ids), n, out, out_dtype,
+                               (long long)ld_out));
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }

@@ -35,6 +35,11 @@ class _Obj:
 
 
 class MyriadEngine:
+    # Inference layout of the LLaMA weights: LoRA A rows appended to the fused qkv weight (the rank-8 update is applied
+    # inside the RoPE kernel) and gate/up rows interleaved in blocks of 64 for the fused SwiGLU GEMM epilogue. The trainer
+    # keeps the plain layout (it needs the pre-activation gate/up values and xa for the backward pass).
+    FUSED_LLAMA = True
+
     def __init__(self, sd, dims: MyriadDims, device="cuda:0", max_batch=8, max_seq=512):
         self.d = dims
         self.dev = torch.device(device)
@@ -136,20 +141,36 @@ class MyriadEngine:
         for i in range(l.layers):
             lp = p + "layers.%d." % i
             L = _Obj()
-            L.wqkv = _h(torch.cat([sd[lp + "self_attn.q_proj.weight"], sd[lp + "self_attn.k_proj.weight"],
-                                   sd[lp + "self_attn.v_proj.weight"]]), dev)
+            qkv_rows = [sd[lp + "self_attn.q_proj.weight"], sd[lp + "self_attn.k_proj.weight"], sd[lp + "self_attn.v_proj.weight"]]
+            pl = "llama_model.base_model.model.model.layers.%d.self_attn." % i
+            if self.FUSED_LLAMA and self.d.lora_r > 0:
+                qkv_rows += [sd[pl + "q_proj.lora_A.default.weight"], sd[pl + "v_proj.lora_A.default.weight"]]
+            L.wqkv = _h(torch.cat(qkv_rows), dev)
+            del qkv_rows
             L.wo = _h(sd[lp + "self_attn.o_proj.weight"], dev)
-            L.wgu = _h(torch.cat([sd[lp + "mlp.gate_proj.weight"], sd[lp + "mlp.up_proj.weight"]]), dev)
+            g_, u_ = _h(sd[lp + "mlp.gate_proj.weight"], dev), _h(sd[lp + "mlp.up_proj.weight"], dev)
+            if self.FUSED_LLAMA:
+                assert l.inter % 64 == 0
+                L.wgu = torch.stack([g_.reshape(l.inter // 64, 64, l.hidden), u_.reshape(l.inter // 64, 64, l.hidden)],
+                                    1).reshape(2 * l.inter, l.hidden).contiguous()
+            else:
+                L.wgu = torch.cat([g_, u_])
+            del g_, u_
             L.wd = _h(sd[lp + "mlp.down_proj.weight"], dev)
             L.n1, L.n2 = _f(sd[lp + "input_layernorm.weight"], dev), _f(sd[lp + "post_attention_layernorm.weight"], dev)
             L.lora = None
             if self.d.lora_r > 0:
-                pl = "llama_model.base_model.model.model.layers.%d.self_attn." % i
                 s = self.d.lora_alpha / self.d.lora_r
                 L.lora = _Obj()
-                L.lora.a = _h(torch.cat([sd[pl + "q_proj.lora_A.default.weight"], sd[pl + "v_proj.lora_A.default.weight"]]), dev)
-                L.lora.bq = _h(sd[pl + "q_proj.lora_B.default.weight"] * s, dev)
-                L.lora.bv = _h(sd[pl + "v_proj.lora_B.default.weight"] * s, dev)
+                L.lora.scale = s
+                if self.FUSED_LLAMA:
+                    assert self.d.lora_r == 8, "the fused RoPE + LoRA kernel is written for the reference's r = 8 (myriad.py:172)"
+                    L.lora.bq = _h(sd[pl + "q_proj.lora_B.default.weight"], dev)
+                    L.lora.bv = _h(sd[pl + "v_proj.lora_B.default.weight"], dev)
+                else:
+                    L.lora.a = _h(torch.cat([sd[pl + "q_proj.lora_A.default.weight"], sd[pl + "v_proj.lora_A.default.weight"]]), dev)
+                    L.lora.bq = _h(sd[pl + "q_proj.lora_B.default.weight"] * s, dev)
+                    L.lora.bv = _h(sd[pl + "v_proj.lora_B.default.weight"] * s, dev)
             W.layers.append(L)
         W.norm = _f(sd[p + "norm.weight"], dev)
         W.lm_head = _h(sd["llama_model.lm_head.weight"], dev)
@@ -305,32 +326,38 @@ class MyriadEngine:
             self._decode_graphs = {}
 
     def _llama_layer(self, L, li, h32, bufs, B, S, pos, kv_len, cache_off, cache_off_dev, Skv, causal):
+        """LlamaDecoderLayer.forward modeling_llama.py:247-299 as 8 launches: RMSNorm -> qkv (+ LoRA A rows) GEMM -> RoPE +
+        LoRA B + KV-cache append -> flash attention -> o_proj GEMM (+ residual) -> RMSNorm -> gate/up GEMM with fused
+        SwiGLU -> down GEMM (+ residual). Weights are static, so each GEMM may prefetch them under the previous kernel."""
         l = self.d.llama
         D, H, dh, T = l.hidden, l.heads, l.head_dim, B * S
-        x16, qkv, ctx, gu, act = bufs
+        x16, qkv, ctx, _, act = bufs
         kc, vc = self.kcache[li], self.vcache[li]
+        ldq = qkv.shape[1]
         K.norm(h32, L.n1, None, l.eps, rms=True, out16=x16)
-        K.gemm(x16, L.wqkv, out=qkv)
-        if L.lora is not None:  # peft LoRA on q_proj / v_proj: += (alpha/r) B (A x), myriad.py:171-178
-            r = self.d.lora_r
-            xa = K.gemm(x16, L.lora.a)
-            K.gemm(xa[:, :r], L.lora.bq, res=qkv[:, :D], out=qkv[:, :D], T=T, K=r)
-            K.gemm(xa[:, r:], L.lora.bv, res=qkv[:, 2 * D:], out=qkv[:, 2 * D:], T=T, K=r)
-        K.rope_cache(qkv, B, S, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, cache_off=cache_off, cache_off_dev=cache_off_dev)
-        cs = (kc.stride(1), kc.stride(0), dh)
-        K.attention(qkv, kc, vc, ctx, B, H, S, Skv, dh, 1.0 / math.sqrt(dh), (3 * D, S * 3 * D, dh), cs, cs, (D, S * D, dh),
-                    causal=causal, q_off=0, kv_len=kv_len)
-        K.gemm(ctx, L.wo, res=h32, out=h32)
+        K.gemm(x16, L.wqkv, out=qkv, w_static=True)
+        lora = (L.lora.bq, L.lora.bv, self.d.lora_r, L.lora.scale) if L.lora is not None else None  # myriad.py:171-178
+        if S == 1 and dh == 128 and kv_len is not None:
+            # decode: rotary + LoRA-B + cache append + attention over the cache in one CUDA-core launch
+            K.decode_attention(qkv, B, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, kv_len, ctx, 1.0 / math.sqrt(dh),
+                               cache_off=cache_off, cache_off_dev=cache_off_dev, lora=lora)
+        else:
+            K.rope_cache(qkv, B, S, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, cache_off=cache_off,
+                         cache_off_dev=cache_off_dev, lora=lora)
+            cs = (kc.stride(1), kc.stride(0), dh)
+            K.attention(qkv, kc, vc, ctx, B, H, S, Skv, dh, 1.0 / math.sqrt(dh), (ldq, S * ldq, dh), cs, cs, (D, S * D, dh),
+                        causal=causal, q_off=0, kv_len=kv_len)
+        K.gemm(ctx, L.wo, res=h32, out=h32, w_static=True)
         K.norm(h32, L.n2, None, l.eps, rms=True, out16=x16)
-        K.gemm(x16, L.wgu, out=gu)
-        K.swiglu(gu, act, T, l.inter)
-        K.gemm(act, L.wd, res=h32, out=h32)
+        K.gemm(x16, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
+        K.gemm(act, L.wd, res=h32, out=h32, w_static=True)
 
     def _llama_bufs(self, T):
         l, dev = self.d.llama, self.dev
-        return (torch.empty(T, l.hidden, device=dev, dtype=F16), torch.empty(T, 3 * l.hidden, device=dev, dtype=F16),
-                torch.empty(T, l.hidden, device=dev, dtype=F16), torch.empty(T, 2 * l.inter, device=dev, dtype=F16),
-                torch.empty(T, l.inter, device=dev, dtype=F16))
+        wq = 3 * l.hidden + (2 * self.d.lora_r if (self.FUSED_LLAMA and self.d.lora_r) else 0)
+        gu = None if self.FUSED_LLAMA else torch.empty(T, 2 * l.inter, device=dev, dtype=F16)
+        return (torch.empty(T, l.hidden, device=dev, dtype=F16), torch.empty(T, wq, device=dev, dtype=F16),
+                torch.empty(T, l.hidden, device=dev, dtype=F16), gu, torch.empty(T, l.inter, device=dev, dtype=F16))
 
     def llama_prefill(self, embeds32, kv_len=None, all_logits=False):
         """embeds32 fp32 [B, S, D] (consumed as the residual stream). kv_len int32 [B] = valid (unpadded) length per
@@ -347,11 +374,11 @@ class MyriadEngine:
         if all_logits:
             x16 = bufs[0]
             K.norm(h32, self.llw.norm, None, l.eps, rms=True, out16=x16)
-            return K.gemm(x16, self.llw.lm_head, out_dtype=F32).reshape(B, S, l.vocab)
+            return K.gemm(x16, self.llw.lm_head, out_dtype=F32, w_static=True).reshape(B, S, l.vocab)
         last = h32.reshape(B, S, D)[:, S - 1]
         x16 = torch.empty(B, D, device=dev, dtype=F16)
         K.norm(last, self.llw.norm, None, l.eps, rms=True, out16=x16)
-        return K.gemm(x16, self.llw.lm_head, out_dtype=F32)
+        return K.gemm(x16, self.llw.lm_head, out_dtype=F32, w_static=True)
 
     # ------------------------------------------------------------------------------------------- decode
     def _decode_step(self, st):
@@ -363,7 +390,7 @@ class MyriadEngine:
         for li, L in enumerate(self.llw.layers):
             self._llama_layer(L, li, st.h32, st.bufs, B, 1, st.pos, st.kv_len, 0, st.cache_off, st.Skv, False)
         K.norm(st.h32, self.llw.norm, None, l.eps, rms=True, out16=st.bufs[0])
-        K.gemm(st.bufs[0], self.llw.lm_head, out=st.logits)
+        K.gemm(st.bufs[0], self.llw.lm_head, out=st.logits, w_static=True)
         K.greedy_step(st.logits, st.state, st.scratch, B, l.vocab, st.max_new, st.min_new, l.eos, st.stops, st.n_stops,
                       st.stop_len)
 
@@ -391,9 +418,11 @@ class MyriadEngine:
         return st
 
     def greedy_decode(self, embeds32, max_new_tokens=90, stop_seqs=((835,), (2277, 29937)), min_new_tokens=1,
-                      use_graph=True):
+                      use_graph=True, sync_every=8):
         """Greedy search from inputs_embeds (all-ones attention mask, as Myriad.generate passes none):
-        prefill, then one token per step. Returns int64 [B, n_new] NEW tokens only (CPU tensor)."""
+        prefill, then one token per step. Returns int64 [B, n_new] NEW tokens only (CPU tensor).
+        The stop decision is taken on the device; the host reads the (step, done) flags only every `sync_every` graph
+        replays, so the GPU runs decode steps back to back. Replays issued after the stop leave the state untouched."""
         dev = self.dev
         B, S, _ = embeds32.shape
         self._ensure_cache(B, S + max_new_tokens)
@@ -430,8 +459,9 @@ class MyriadEngine:
                     st.graph_nodes = K.launch_count() - n0
                     st.graph = g
                     st.state.copy_(snap)  # capture does not execute; replay from the snapshot
-                st.graph.replay()
-                K.note_graph_replay(st.graph_nodes)
+                for _ in range(max(1, min(sync_every, max_new_tokens - step))):
+                    st.graph.replay()
+                    K.note_graph_replay(st.graph_nodes)
             else:
                 self._decode_step(st)
         n = int(st.state[0].item())

@@ -46,6 +46,7 @@ class GemmArgs(ctypes.Structure):
         ("x_bs0", ctypes.c_int64), ("x_bs1", ctypes.c_int64), ("w_bs0", ctypes.c_int64), ("w_bs1", ctypes.c_int64),
         ("o_bs0", ctypes.c_int64), ("o_bs1", ctypes.c_int64),
         ("alpha_set", ctypes.c_int32), ("alpha", ctypes.c_float),
+        ("pdl", ctypes.c_int32), ("w_static", ctypes.c_int32),
     ]
 
 
@@ -53,18 +54,19 @@ _ws_cache = {}
 
 
 def workspace(nbytes, device):
-    """Grow-only per-device scratch buffer (split-K partials etc.). Owned by PyTorch, lent to the library."""
+    """Grow-only per-device scratch buffer (arrival counters + split-tile partials). Owned by PyTorch, lent to the
+    library; zero-filled on creation because the counters at its head must start at zero (include/myriad_b200.h)."""
     key = (device.index if device.index is not None else torch.cuda.current_device())
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(nbytes, 96 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 
 
 def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.float16, scale_cols=0, scale=1.0,
          round_acc=False, x_mn_major=False, w_mn_major=False, T=None, F=None, K=None, bn_hint=0, ksplit_hint=0,
-         out_group_rows=0, out_group_stride=0, ldo=None, ldx=None, ldw=None, batch=None, alpha=None):
+         out_group_rows=0, out_group_stride=0, ldo=None, ldx=None, ldw=None, batch=None, alpha=None, pdl=True, w_static=False):
     # batch = (nb0, nb1, (x_bs0, x_bs1), (w_bs0, w_bs1), (o_bs0, o_bs1)): independent problems, element strides
     """out[t, f] = epilogue(sum_k x[t, k] * w[f, k]);  x: [T, K] fp16 (row stride may exceed K), w: [F, K] fp16."""
     assert x.dtype == torch.float16 and w.dtype == torch.float16
@@ -77,8 +79,8 @@ def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.floa
     if F is None:
         F = w.shape[0] if not w_mn_major else w.shape[1]
     if out is None:
-        out = torch.empty((T, F), dtype=out_dtype, device=x.device)
-    ws = workspace(64 << 20, x.device)
+        out = torch.empty((T, F // 2 if act == ACT_SWIGLU else F), dtype=out_dtype, device=x.device)
+    ws = workspace(96 << 20, x.device)
     a = GemmArgs()
     a.x, a.ldx = x.data_ptr(), (ldx if ldx is not None else x.stride(0))
     a.w, a.ldw = w.data_ptr(), (ldw if ldw is not None else w.stride(0))
@@ -106,11 +108,13 @@ def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.floa
     a.out_group_rows, a.out_group_stride = out_group_rows, out_group_stride
     if alpha is not None:
         a.alpha_set, a.alpha = 1, alpha
+    a.pdl, a.w_static = int(pdl), int(w_static)
     check(lib().myr_gemm_f16(ctypes.byref(a), _stream()), "myr_gemm_f16")
     return out
 
 
 ACT_RELU = 2
+ACT_SWIGLU = 3
 
 
 class AttnArgs(ctypes.Structure):
@@ -190,10 +194,12 @@ class RopeArgs(ctypes.Structure):
         ("cos", ctypes.c_void_p), ("sin", ctypes.c_void_p),
         ("kcache", ctypes.c_void_p), ("vcache", ctypes.c_void_p), ("c_ts", ctypes.c_int64), ("c_bs", ctypes.c_int64),
         ("cache_off", ctypes.c_int32), ("cache_off_dev", ctypes.c_void_p),
+        ("lora_bq", ctypes.c_void_p), ("lora_bv", ctypes.c_void_p), ("lora_r", ctypes.c_int32), ("lora_scale", ctypes.c_float),
     ]
 
 
-def rope_cache(qkv, B, S, H, dh, pos, cos, sin, kcache, vcache, cache_off=0, cache_off_dev=None):
+def rope_cache(qkv, B, S, H, dh, pos, cos, sin, kcache, vcache, cache_off=0, cache_off_dev=None, lora=None):
+    """lora = (B_q fp16 [H*dh, r], B_v fp16 [H*dh, r], r, scale): xa = x A^T is read from qkv[:, 3*H*dh:3*H*dh + 2r]."""
     a = RopeArgs()
     a.qkv, a.ldq = qkv.data_ptr(), qkv.stride(0)
     a.B, a.S, a.H, a.dh = B, S, H, dh
@@ -203,7 +209,47 @@ def rope_cache(qkv, B, S, H, dh, pos, cos, sin, kcache, vcache, cache_off=0, cac
     a.c_ts, a.c_bs = kcache.stride(1), kcache.stride(0)
     a.cache_off = cache_off
     a.cache_off_dev = cache_off_dev.data_ptr() if cache_off_dev is not None else None
+    if lora is not None:
+        bq, bv, r, scale = lora
+        assert bq.dtype == torch.float16 and bv.dtype == torch.float16 and bq.is_contiguous() and bv.is_contiguous()
+        a.lora_bq, a.lora_bv, a.lora_r, a.lora_scale = bq.data_ptr(), bv.data_ptr(), r, scale
     check(lib().myr_rope_cache(ctypes.byref(a), _stream()), "myr_rope_cache")
+
+
+class DecodeAttnArgs(ctypes.Structure):
+    _fields_ = [
+        ("qkv", ctypes.c_void_p), ("ldq", ctypes.c_int64),
+        ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("dh", ctypes.c_int32),
+        ("pos", ctypes.c_void_p), ("cos", ctypes.c_void_p), ("sin", ctypes.c_void_p),
+        ("kcache", ctypes.c_void_p), ("vcache", ctypes.c_void_p), ("c_ts", ctypes.c_int64), ("c_bs", ctypes.c_int64),
+        ("cache_len", ctypes.c_int32),
+        ("cache_off", ctypes.c_int32), ("cache_off_dev", ctypes.c_void_p),
+        ("kv_len", ctypes.c_void_p),
+        ("lora_bq", ctypes.c_void_p), ("lora_bv", ctypes.c_void_p), ("lora_r", ctypes.c_int32), ("lora_scale", ctypes.c_float),
+        ("scale", ctypes.c_float),
+        ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64),
+    ]
+
+
+def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, scale, cache_off=0, cache_off_dev=None, lora=None):
+    """One new token per sequence: LoRA-B + RoPE + KV-cache append + attention over the cache in one launch."""
+    a = DecodeAttnArgs()
+    a.qkv, a.ldq = qkv.data_ptr(), qkv.stride(0)
+    a.B, a.H, a.dh = B, H, dh
+    assert pos.dtype == torch.int32 and kv_len.dtype == torch.int32
+    a.pos, a.cos, a.sin = pos.data_ptr(), cos.data_ptr(), sin.data_ptr()
+    a.kcache, a.vcache = kcache.data_ptr(), vcache.data_ptr()
+    a.c_ts, a.c_bs, a.cache_len = kcache.stride(1), kcache.stride(0), kcache.shape[1]
+    a.cache_off = cache_off
+    a.cache_off_dev = cache_off_dev.data_ptr() if cache_off_dev is not None else None
+    a.kv_len = kv_len.data_ptr()
+    if lora is not None:
+        bq, bv, r, s = lora
+        a.lora_bq, a.lora_bv, a.lora_r, a.lora_scale = bq.data_ptr(), bv.data_ptr(), r, s
+    a.scale = scale
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    check(lib().myr_decode_attention(ctypes.byref(a), _stream()), "myr_decode_attention")
+    return out
 
 
 def _i64(v):

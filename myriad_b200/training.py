@@ -32,6 +32,8 @@ def _numel(shape):
 
 
 class MyriadTrainer(MyriadEngine):
+    FUSED_LLAMA = False  # plain weight layout: the backward needs the pre-activation gate/up values and xa = x A^T
+
     def __init__(self, sd, dims, device="cuda:0", max_batch=8, max_seq=512, loss_scale=1024.0, lr=1e-4, betas=(0.9, 0.999),
                  eps=1e-8, weight_decay=0.05):
         self._sd_for_flat = sd

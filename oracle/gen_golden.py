@@ -275,7 +275,7 @@ def gen_mid():
 def _sample(t, n=4096):
     """Deterministic subsample of a gradient tensor (flat stride) so fixtures stay small."""
     f = t.detach().reshape(-1)
-    step = max(1, f.numel() // n)
+    step = max(1, f.numel() // n) | 1  # odd stride: does not alias with the power-of-two tensor dims
     return f[::step][:n].clone()
 
 
@@ -336,6 +336,11 @@ def gen_mid_train():
             arrs["loss_stage%d" % stage] = oloss
             for k, v in ograds.items():
                 arrs["s%d:%s" % (stage, k)] = _sample(v)
+            # conv-stack gradients under fp16 activation storage (restated emulation; see myriad_oracle.CONV_FP16_ACTS)
+            _, egrads = O.train_grads(sd, d, image, maps, stage, ids_b, ids_a, text, tmask, conv_fp16=True)
+            for k, v in egrads.items():
+                if ".meta_net." in k:
+                    arrs["e%d:%s" % (stage, k)] = _sample(v)
         _save("myriad_mid_train" + ("_lora" if lora_r else ""), seed=SEED, input_seed=13, lora_r=lora_r, text=text, text_mask=tmask, **arrs)
 
 

@@ -100,12 +100,34 @@ def lora_adaptor(sd, x, p="expert_adaptor."):
     return x + linear(linear(x, sd[p + "conv1.weight"]), sd[p + "conv2.weight"])
 
 
+class _RoundFp16(torch.autograd.Function):
+    """fp16 storage of an activation (forward) and of its gradient (backward), everything else fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.half().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.half().float()
+
+
+# When True, conv_stack stores each post-ReLU map in fp16 — the device path's (and the reference CUDA autocast path's)
+# storage precision. The only place on the hot path where that matters qualitatively: max-pool arg-max / ReLU gates are
+# discrete, so fp16 storage flips ~1e-3 of them and the weight gradients (random-sign sums over positions) move by 3-10 %
+# against the pure-fp32 restatement. tests/test_training_gpu.py compares the device conv gradients with this emulation
+# (tight) and with the pure fp32 oracle (loose); every other comparison uses the pure fp32 oracle.
+CONV_FP16_ACTS = False
+
+
 def conv_stack(sd, p, maps):
     """The shared 5 x [conv3x3 pad1, ReLU, maxpool2] trunk, networks.py:98-122 / 159-182. -> [B,1024,7,7]"""
     x = maps
     for idx in CONV_IDX:
-        x = F.conv2d(x, sd["%smeta_net.%d.weight" % (p, idx)], sd["%smeta_net.%d.bias" % (p, idx)], padding=1)
-        x = F.max_pool2d(F.relu(x), 2)
+        x = F.relu(F.conv2d(x, sd["%smeta_net.%d.weight" % (p, idx)], sd["%smeta_net.%d.bias" % (p, idx)], padding=1))
+        if CONV_FP16_ACTS:
+            x = _RoundFp16.apply(x)
+        x = F.max_pool2d(x, 2)
     return x
 
 
@@ -303,8 +325,18 @@ def myriad_loss(sd, image, maps, stage, ids_before, ids_after, text_ids, text_ma
     return clamp_ce_loss(logits, targets), logits
 
 
-def train_grads(sd, d, image, maps, stage, ids_b, ids_a, text, tmask):
-    """Loss + gradients of every trainable tensor (runner_base.py:111-119) by autograd over the oracle restatement."""
+def train_grads(sd, d, image, maps, stage, ids_b, ids_a, text, tmask, conv_fp16=False):
+    """Loss + gradients of every trainable tensor (runner_base.py:111-119) by autograd over the oracle restatement.
+    conv_fp16: emulate fp16 storage of the conv-stack activations (see CONV_FP16_ACTS)."""
+    global CONV_FP16_ACTS
+    CONV_FP16_ACTS = bool(conv_fp16)
+    try:
+        return _train_grads(sd, d, image, maps, stage, ids_b, ids_a, text, tmask)
+    finally:
+        CONV_FP16_ACTS = False
+
+
+def _train_grads(sd, d, image, maps, stage, ids_b, ids_a, text, tmask):
     keys = [k for k in sd if k.startswith(("expert_adaptor.", "VEInstructor.", "VETokenizer.")) or ".lora_" in k]
     sd2 = dict(sd)
     for k in keys:

@@ -88,6 +88,70 @@ def test_gemm_mn_major_operands(K):
     close(K.gemm(xt, wt, x_mn_major=True, w_mn_major=True, T=T, F=F, K=Kd, bn_hint=128), ref, 2e-3, "both mn-major")
 
 
+def _interleave64(gate, up):
+    """[I, K] gate and up rows -> [2I, K] in blocks of 64: gate 0..63, up 0..63, gate 64..127, ... (MYR_ACT_SWIGLU layout)."""
+    I, Kd = gate.shape
+    return torch.stack([gate.reshape(I // 64, 64, Kd), up.reshape(I // 64, 64, Kd)], 1).reshape(2 * I, Kd)
+
+
+@pytest.mark.parametrize("T,I,Kd", [(4, 1024, 512), (4, 11008, 4096), (33, 512, 256), (300, 512, 256), (524, 2048, 1024)])
+def test_gemm_swiglu_epilogue(K, T, I, Kd):
+    """gate/up projection with the SwiGLU of modeling_llama.py:139-140 fused (both operand arrangements, split and
+    unsplit tiles); rounding points identical to the unfused gemm + myr_swiglu path."""
+    x = rnd(T, Kd, seed=1).half()
+    g, u = (rnd(I, Kd, seed=2) / Kd ** 0.5).half(), (rnd(I, Kd, seed=3) / Kd ** 0.5).half()
+    xd = x.to(dev())
+    y = K.gemm(xd, _interleave64(g, u).to(dev()), act=K.ACT_SWIGLU)
+    assert y.shape == (T, I)
+    gu = K.gemm(xd, torch.cat([g, u]).to(dev()))
+    ref = torch.empty(T, I, device=dev(), dtype=torch.float16)
+    K.swiglu(gu, ref, T, I)
+    # same rounding points as the unfused path; the k-ranges of split tiles differ between the two weight layouts, so the
+    # fp32 sums may differ in their last bit and the fp16 results by one ulp
+    close(y, ref, 1e-3, "fused vs unfused SwiGLU")
+    assert (y != ref).float().mean().item() < 0.02
+    gf, uf = x.float() @ g.float().t(), x.float() @ u.float().t()
+    close(y, torch.nn.functional.silu(gf) * uf, 3e-3, "swiglu vs fp32")
+
+
+@pytest.mark.parametrize("T,F,Kd", [(4, 22016, 4096), (4, 4096, 11008), (1, 32000, 4096), (16, 12304, 4096), (48, 768, 1408),
+                                    (100, 256, 8192), (200, 512, 16384)])
+def test_gemm_stream_k(K, T, F, Kd):
+    """Shapes whose tiles are shared between CTAs (equal k-block ranges): the finisher's fixed-order sum must make the
+    result reproducible run to run, and the arrival counters must be left clean for the next launch."""
+    x, w = rnd(T, Kd, seed=1).half().to(dev()), (rnd(F, Kd, seed=2) / Kd ** 0.5).half().to(dev())
+    r32 = rnd(T, F, seed=4).to(dev())
+    ref = x.float() @ w.float().t() + r32
+    y1 = K.gemm(x, w, res=r32, out_dtype=torch.float32)
+    y2 = K.gemm(x, w, res=r32, out_dtype=torch.float32)
+    close(y1, ref, 1e-3, "stream-K")
+    assert torch.equal(y1, y2), "split tiles must reduce deterministically"
+    y3 = K.gemm(x, w, res=r32, out_dtype=torch.float32, ksplit_hint=1)
+    close(y3, ref, 1e-3, "data-parallel")
+
+
+def test_gemm_small_t_mn_major_and_pdl_chain(K):
+    """T <= 64 with MN-major operands (dgrad / wgrad forms in the lanes = features arrangement) and a chain of dependent
+    GEMMs launched back to back with programmatic dependent launch (each consumes the previous one's output)."""
+    T, F, Kd = 48, 320, 256
+    x, w = rnd(T, Kd, seed=1).half(), (rnd(F, Kd, seed=2) / 16).half()
+    ref = x.float() @ w.float().t()
+    xd, wd = x.to(dev()), w.to(dev())
+    xt, wt = xd.t().contiguous(), wd.t().contiguous()
+    close(K.gemm(xd, wt, w_mn_major=True, F=F, K=Kd), ref, 2e-3, "w mn-major, small T")
+    close(K.gemm(xt, wd, x_mn_major=True, T=T, K=Kd), ref, 2e-3, "x mn-major, small T")
+    close(K.gemm(xt, wt, x_mn_major=True, w_mn_major=True, T=T, F=F, K=Kd), ref, 2e-3, "both mn-major, small T")
+    D = 1024
+    ws = [(rnd(D, D, seed=10 + i) / D ** 0.5).half().to(dev()) for i in range(6)]
+    for T in (4, 200):
+        h = rnd(T, D, seed=3).half().to(dev())
+        cur, ref = h, h.float()
+        for wi in ws:
+            cur = K.gemm(cur, wi, w_static=True)
+            ref = (ref @ wi.float().t()).half().float()
+        close(cur, ref, 5e-3, "pdl chain T=%d" % T)
+
+
 # ------------------------------------------------------------------------------------------- attention
 def ref_attention(q, k, v, scale, causal=False, q_off=0, kv_len=None):
     # q [B,Sq,H,dh], k/v [B,Skv,H,dh] fp32
@@ -293,3 +357,57 @@ def test_greedy_step(K):
     assert toks[1, :3].tolist() == [11, 9, 9]      # eos suppressed at step 0 only
     assert int(s[0]) == 3 and int(s[1]) == 1        # stopped by row-0 stop sequence (77, 88)
     assert s[4 + 2 * B:4 + 3 * B].tolist() == [13] * B and s[4 + 3 * B:4 + 4 * B].tolist() == [12] * B and int(s[2]) == 12
+
+
+@pytest.mark.parametrize("lora", [False, True])
+def test_decode_attention_matches_rope_plus_flash(K, O, lora):
+    """myr_decode_attention (one launch per decode step and layer) against the prefill pair myr_rope_cache + myr_attention_fwd
+    on the same cache, and against the oracle's rotary / attention arithmetic."""
+    torch.manual_seed(4)
+    B, H, dh, Smax, r = 3, 4, 128, 96, 8
+    D = H * dh
+    ldq = 3 * D + (2 * r if lora else 0)
+    past = [40, 57, 1]
+    kc = (torch.randn(B, Smax, D) * 0.5).half()
+    vc = (torch.randn(B, Smax, D) * 0.5).half()
+    qkv = (torch.randn(B, ldq) * 0.5).half()
+    bq, bv = (torch.randn(D, r) * 0.05).half(), (torch.randn(D, r) * 0.05).half()
+    off = 60  # the graph-replayed decode writes every row's new token to the same slot; rows are right-aligned by kv_len
+    # make "past" keys of each row live in slots [off - past, off)
+    pos = torch.tensor([p for p in past], dtype=torch.int32)
+    kv_len = torch.tensor([off + 1] * B, dtype=torch.int32)
+    cos, sin = O.rope_tables(dh, 256)
+    half = dh // 2
+    cosd, sind = cos[:, :half].contiguous().to(dev()), sin[:, :half].contiguous().to(dev())
+    lo = (bq.to(dev()), bv.to(dev()), r, 2.0) if lora else None
+    # reference pair on its own copy of the cache
+    kc1, vc1, q1 = kc.to(dev()).clone(), vc.to(dev()).clone(), qkv.to(dev()).clone()
+    K.rope_cache(q1, B, 1, H, dh, pos.to(dev()), cosd, sind, kc1, vc1, cache_off=off, lora=lo)
+    ref = torch.empty(B, D, device=dev(), dtype=torch.float16)
+    cs = (kc1.stride(1), kc1.stride(0), dh)
+    K.attention(q1, kc1, vc1, ref, B, H, 1, Smax, dh, 1.0 / math.sqrt(dh), (ldq, ldq, dh), cs, cs, (D, D, dh), causal=False,
+                kv_len=kv_len.to(dev()))
+    kc2, vc2 = kc.to(dev()).clone(), vc.to(dev()).clone()
+    out = torch.empty(B, D, device=dev(), dtype=torch.float16)
+    K.decode_attention(qkv.to(dev()), B, H, dh, pos.to(dev()), cosd, sind, kc2, vc2, kv_len.to(dev()), out, 1.0 / math.sqrt(dh),
+                       cache_off=off, lora=lo)
+    close(kc2, kc1, 1e-3, "appended k")
+    close(vc2, vc1, 1e-3, "appended v")
+    print("cache append: %d k / %d v values differ in the last bit from myr_rope_cache" % (
+        int((kc1 != kc2).sum()), int((vc1 != vc2).sum())))
+    close(out, ref, 2e-3, "decode attention vs rope+flash")
+    # oracle arithmetic (fp32)
+    x = qkv.float()
+    q, k, v = x[:, :D], x[:, D:2 * D], x[:, 2 * D:3 * D]
+    if lora:
+        q = q + 2.0 * x[:, 3 * D:3 * D + r] @ bq.float().t()
+        v = v + 2.0 * x[:, 3 * D + r:] @ bv.float().t()
+    q = O.apply_rope(q.reshape(B, 1, H, dh).transpose(1, 2), cos, sin, pos.long()[:, None])
+    k = O.apply_rope(k.reshape(B, 1, H, dh).transpose(1, 2), cos, sin, pos.long()[:, None])
+    kk = kc.float().reshape(B, Smax, H, dh).transpose(1, 2).clone()
+    vv = vc.float().reshape(B, Smax, H, dh).transpose(1, 2).clone()
+    kk[:, :, off] = k[:, :, 0]
+    vv[:, :, off] = v.reshape(B, H, dh)
+    s = (q @ kk[:, :, :off + 1].transpose(-1, -2)) / math.sqrt(dh)
+    o = (torch.softmax(s, -1) @ vv[:, :, :off + 1]).transpose(1, 2).reshape(B, D)
+    close(out, o, 3e-3, "decode attention vs oracle arithmetic")
