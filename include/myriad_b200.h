@@ -167,6 +167,36 @@ typedef struct {
 } myr_decode_attn_args;
 int myr_decode_attention(const myr_decode_attn_args* args, void* stream);
 
+/* ---- persistent decode-step kernel ----------------------------------------------------------------------------------
+ * One launch = one greedy-decode step of the whole LLaMA stack for T <= 16 sequences (modeling_llama.py:466-716 with a
+ * single new token per sequence): the caller describes the step as a list of ops; myr_mega_plan turns it into a device
+ * blob (tensor maps + op records; copy it to the device verbatim, 64-byte aligned) and reports the zero-initialised
+ * workspace it needs; myr_mega_launch runs it. Ops execute in list order; op i may read what ops < i wrote.
+ *   MYR_MEGA_GEMM : out = epi(x[T,K] w[F,K]^T), weights streamed once (stream-K over all SMs). epi: MYR_MEGA_F16 store fp16,
+ *                   MYR_MEGA_RES32 out(fp32) += acc (residual stream, in place), MYR_MEGA_SWIGLU (64-row interleaved gate/up,
+ *                   fp16 out [T, F/2]), MYR_MEGA_F32 store fp32.
+ *   MYR_MEGA_ATTN : myr_decode_attention semantics (LoRA-B + RoPE + cache append + attention), one CTA per (head, row).
+ *   MYR_MEGA_EMBED: h32[t,:] = table[ids[t],:] (embedding gather, ids int32 on the device).
+ * Any op may carry a tail executed once the op is complete: norm_dst(fp16)[t,:] = RMSNorm(norm_src(fp32)[t,:]) * gamma for
+ * t < norm_rows (modeling_llama.py:66-74) — the fp16 operand of the next GEMM. */
+enum myr_mega_kind { MYR_MEGA_GEMM = 0, MYR_MEGA_ATTN = 1, MYR_MEGA_EMBED = 2 };
+enum myr_mega_epi { MYR_MEGA_F16 = 0, MYR_MEGA_RES32 = 1, MYR_MEGA_SWIGLU = 2, MYR_MEGA_F32 = 3 };
+typedef struct {
+  int32_t kind, epi;
+  const void* x; int64_t ldx; const void* w; int64_t ldw; int32_t T, F, K;
+  void* out; int64_t ldo;
+  const void* norm_src; void* norm_dst; const void* gamma; float eps; int32_t D; int32_t norm_rows;
+  const void* table; const void* ids; void* h32;
+  myr_decode_attn_args attn;
+} myr_mega_op;
+size_t myr_mega_plan_bytes(int32_t n_ops);
+int myr_mega_plan(const myr_mega_op* ops, int32_t n_ops, void* host_blob, size_t blob_bytes, size_t* workspace_bytes,
+                  int32_t* n_tile_counters);
+/* trace: optional device int64 [3 * n_ops] (%globaltimer ns per op: completed | first CTA saw its input | first CTA drained a
+ * tile) for profiling the op chain; NULL in production. */
+int myr_mega_launch(const void* dev_blob, int32_t n_ops, void* workspace, size_t workspace_bytes, int32_t n_tile_counters,
+                    void* trace, void* stream);
+
 /* SwiGLU modeling_llama.py:139-140: out[t, i] = silu(gate_up[t, i]) * gate_up[t, I + i] (fp16). */
 int myr_swiglu(const void* gate_up, int64_t ld_gu, void* out, int64_t ld_out, int32_t T, int32_t I, void* stream);
 /* Embedding gather myriad.py:308-311: out[r, :] = table[ids[r], :]; table fp16 [V, D]; ids int32 or int64 (device). */

@@ -26,6 +26,8 @@ def lib():
         _lib.myr_last_error.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         _lib.myr_device_sm_count.restype = ctypes.c_int
         _lib.myr_launch_count.restype = ctypes.c_ulonglong
+        _lib.myr_mega_plan_bytes.restype = ctypes.c_size_t
+        _lib.myr_gemm_workspace_bytes.restype = ctypes.c_size_t
     return _lib
 
 

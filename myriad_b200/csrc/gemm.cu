@@ -304,6 +304,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // lanes = features: A is a weight matrix read exactly once -> evict-first keeps activations / partial tiles in L2
+      const uint64_t pol_a = p.row_mode ? 0ull : l2_policy_evict_first();
       // weight (A) tiles of the first ring fill do not depend on the previous kernel: issue them before the PDL wait
       int pre = 0;
       if (p.w_static) {
@@ -314,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kb = s.kb0; kb < s.kb1 && pre < p.num_stages; ++kb, ++pre) {
             uint8_t* sa = smem + pre * p.stage_bytes;
             mbar_arrive_expect_tx(&full[pre], tx_bytes);
-            tma_load_4d(sa, &tmA, &full[pre], kb * BK, c.m0, c.b1, c.b0);
+            tma_load_4d_hint(sa, &tmA, &full[pre], kb * BK, c.m0, c.b1, c.b0, pol_a);
           }
         }
       }
@@ -331,7 +333,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], tx_bytes);
             if (!p.a_mn) {
-              tma_load_4d(sa, &tmA, &full[stage], kb * BK, c.m0, c.b1, c.b0);
+              if (p.row_mode)
+                tma_load_4d(sa, &tmA, &full[stage], kb * BK, c.m0, c.b1, c.b0);
+              else
+                tma_load_4d_hint(sa, &tmA, &full[stage], kb * BK, c.m0, c.b1, c.b0, pol_a);
             } else {
               tma_load_4d(sa, &tmA, &full[stage], c.m0, kb * BK, c.b1, c.b0);
               tma_load_4d(sa + 8192, &tmA, &full[stage], c.m0 + 64, kb * BK, c.b1, c.b0);

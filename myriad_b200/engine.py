@@ -49,6 +49,11 @@ class MyriadEngine:
         self._prep_qformer(sd)
         self._prep_llama(sd)
         self._decode_graphs = {}
+        # MYR_MEGA=1: one persistent kernel per decode step (decode_mega.cu) instead of ~230 graph-captured launches. Measured
+        # on B200: 4.11 ms/step against 3.70 ms/step for the PDL-chained multi-kernel step, so it is opt-in;
+        # tests/test_engine_gpu.py keeps the two paths bit-identical.
+        import os
+        self.use_mega = os.environ.get("MYR_MEGA", "0") == "1"
 
     # ------------------------------------------------------------------------------------------ weights
     def _prep_vit(self, sd):
@@ -394,6 +399,38 @@ class MyriadEngine:
         K.greedy_step(st.logits, st.state, st.scratch, B, l.vocab, st.max_new, st.min_new, l.eos, st.stops, st.n_stops,
                       st.stop_len)
 
+    def _mega_plan(self, st):
+        """Op list of one decode step for the persistent kernel (kernels.MegaPlan): embedding gather + first RMSNorm, then
+        per layer qkv(+LoRA A) GEMM -> attention -> o_proj (+residual, tail RMSNorm) -> gate/up + SwiGLU -> down_proj
+        (+residual, tail RMSNorm of the next layer / final norm), and lm_head. Same buffers and weights as _decode_step."""
+        l, W = self.d.llama, self.llw
+        B = st.B
+        x16, qkv, ctx, _, act = st.bufs
+        ops = [K.mega_embed(W.embed, st.cur_tok, st.h32, norm=(st.h32, x16, W.layers[0].n1, l.eps))]
+        for li, L in enumerate(W.layers):
+            kc, vc = self.kcache[li], self.vcache[li]
+            lora = (L.lora.bq, L.lora.bv, self.d.lora_r, L.lora.scale) if L.lora is not None else None
+            nxt = W.layers[li + 1].n1 if li + 1 < len(W.layers) else W.norm
+            ops += [K.mega_gemm(x16, L.wqkv, qkv, K.MEGA_F16),
+                    K.mega_attn(qkv, B, l.heads, l.head_dim, st.pos, W.cos, W.sin, kc, vc, st.kv_len, ctx, 1.0 / math.sqrt(l.head_dim),
+                                st.cache_off, lora=lora),
+                    K.mega_gemm(ctx, L.wo, st.h32, K.MEGA_RES32, norm=(st.h32, x16, L.n2, l.eps)),
+                    K.mega_gemm(x16, L.wgu, act, K.MEGA_SWIGLU),
+                    K.mega_gemm(act, L.wd, st.h32, K.MEGA_RES32, norm=(st.h32, x16, nxt, l.eps))]
+        ops.append(K.mega_gemm(x16, W.lm_head, st.logits, K.MEGA_F32))
+        return K.MegaPlan(ops, self.dev)
+
+    def _mega_ok(self, B, Skv):
+        l = self.d.llama
+        return (self.FUSED_LLAMA and self.use_mega and B <= 8 and l.head_dim == 128 and Skv <= 4096 and l.hidden % 8 == 0
+                and (self.d.lora_r in (0, 8)))
+
+    def _decode_step_mega(self, st):
+        l = self.d.llama
+        st.mega.launch()
+        K.greedy_step(st.logits, st.state, st.scratch, st.B, l.vocab, st.max_new, st.min_new, l.eos, st.stops, st.n_stops,
+                      st.stop_len)
+
     def _decode_state(self, B, max_new, min_new, stop_seqs, Skv):
         l, dev = self.d.llama, self.dev
         st = _Obj()
@@ -415,6 +452,7 @@ class MyriadEngine:
         st.bufs = self._llama_bufs(B)
         st.logits = torch.empty(B, l.vocab, device=dev, dtype=F32)
         st.graph = None
+        st.mega = self._mega_plan(st) if self._mega_ok(B, Skv) else None
         return st
 
     def greedy_decode(self, embeds32, max_new_tokens=90, stop_seqs=((835,), (2277, 29937)), min_new_tokens=1,
@@ -447,15 +485,16 @@ class MyriadEngine:
             if done:
                 break
             if use_graph:
+                step_fn = self._decode_step_mega if st.mega is not None else self._decode_step
                 if st.graph is None:
                     snap = st.state.clone()
-                    self._decode_step(st)  # warm-up (sets function attributes, sizes the split-K workspace)
+                    step_fn(st)  # warm-up (sets function attributes, sizes the split-K workspace)
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     st.state.copy_(snap)
                     n0 = K.launch_count()
                     with torch.cuda.graph(g):
-                        self._decode_step(st)
+                        step_fn(st)
                     st.graph_nodes = K.launch_count() - n0
                     st.graph = g
                     st.state.copy_(snap)  # capture does not execute; replay from the snapshot

@@ -252,6 +252,97 @@ def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, 
     return out
 
 
+MEGA_GEMM, MEGA_ATTN, MEGA_EMBED = 0, 1, 2
+MEGA_F16, MEGA_RES32, MEGA_SWIGLU, MEGA_F32 = 0, 1, 2, 3
+
+
+class MegaOp(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32), ("epi", ctypes.c_int32),
+        ("x", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("w", ctypes.c_void_p), ("ldw", ctypes.c_int64),
+        ("T", ctypes.c_int32), ("F", ctypes.c_int32), ("K", ctypes.c_int32),
+        ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64),
+        ("norm_src", ctypes.c_void_p), ("norm_dst", ctypes.c_void_p), ("gamma", ctypes.c_void_p), ("eps", ctypes.c_float),
+        ("D", ctypes.c_int32), ("norm_rows", ctypes.c_int32),
+        ("table", ctypes.c_void_p), ("ids", ctypes.c_void_p), ("h32", ctypes.c_void_p),
+        ("attn", DecodeAttnArgs),
+    ]
+
+
+def _mega_tail(op, norm):
+    if norm is not None:
+        src, dst, gamma, eps = norm
+        assert src.dtype == torch.float32 and dst.dtype == torch.float16 and gamma.dtype == torch.float32
+        assert src.is_contiguous() and dst.is_contiguous()
+        op.norm_src, op.norm_dst, op.gamma, op.eps = src.data_ptr(), dst.data_ptr(), gamma.data_ptr(), eps
+        op.D, op.norm_rows = src.shape[1], src.shape[0]
+
+
+def mega_gemm(x, w, out, epi, norm=None):
+    """x fp16 [T, K], w fp16 [F, K], out [T, F] (or [T, F/2] for SwiGLU). norm = (src32, dst16, gamma, eps) op tail."""
+    op = MegaOp()
+    op.kind, op.epi = MEGA_GEMM, epi
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.stride(1) == 1 and w.stride(1) == 1
+    op.x, op.ldx, op.w, op.ldw = x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0)
+    op.T, op.F, op.K = x.shape[0], w.shape[0], w.shape[1]
+    assert x.shape[1] == w.shape[1]
+    assert out.dtype == (torch.float16 if epi in (MEGA_F16, MEGA_SWIGLU) else torch.float32)
+    op.out, op.ldo = out.data_ptr(), out.stride(0)
+    _mega_tail(op, norm)
+    return op
+
+
+def mega_embed(table, ids, h32, norm=None):
+    op = MegaOp()
+    op.kind = MEGA_EMBED
+    assert table.dtype == torch.float16 and ids.dtype == torch.int32 and h32.dtype == torch.float32 and h32.is_contiguous()
+    op.table, op.ids, op.h32, op.T, op.D = table.data_ptr(), ids.data_ptr(), h32.data_ptr(), ids.numel(), table.shape[1]
+    _mega_tail(op, norm)
+    return op
+
+
+def mega_attn(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, scale, cache_off_dev, lora=None):
+    op = MegaOp()
+    op.kind = MEGA_ATTN
+    a = op.attn
+    a.qkv, a.ldq = qkv.data_ptr(), qkv.stride(0)
+    a.B, a.H, a.dh = B, H, dh
+    a.pos, a.cos, a.sin = pos.data_ptr(), cos.data_ptr(), sin.data_ptr()
+    a.kcache, a.vcache = kcache.data_ptr(), vcache.data_ptr()
+    a.c_ts, a.c_bs, a.cache_len = kcache.stride(1), kcache.stride(0), kcache.shape[1]
+    a.cache_off_dev = cache_off_dev.data_ptr()
+    a.kv_len = kv_len.data_ptr()
+    if lora is not None:
+        bq, bv, r, s = lora
+        a.lora_bq, a.lora_bv, a.lora_r, a.lora_scale = bq.data_ptr(), bv.data_ptr(), r, s
+    a.scale = scale
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    return op
+
+
+class MegaPlan:
+    """Device blob (tensor maps + op records) and zeroed workspace of one persistent decode-step launch. Holds references
+    to nothing: the caller keeps every tensor named by the ops alive."""
+
+    def __init__(self, ops, device):
+        n = len(ops)
+        arr = (MegaOp * n)(*ops)
+        nbytes = lib().myr_mega_plan_bytes(n)
+        host = torch.zeros(nbytes + 64, dtype=torch.uint8)
+        off = (-host.data_ptr()) % 64
+        ws_bytes, n_cnt = ctypes.c_size_t(0), ctypes.c_int32(0)
+        check(lib().myr_mega_plan(arr, n, ctypes.c_void_p(host.data_ptr() + off), ctypes.c_size_t(nbytes), ctypes.byref(ws_bytes),
+                                  ctypes.byref(n_cnt)), "myr_mega_plan")
+        self.n_ops, self.n_counters = n, n_cnt.value
+        self.blob = host[off:off + nbytes].to(device)
+        assert self.blob.data_ptr() % 64 == 0
+        self.workspace = torch.zeros(max(ws_bytes.value, 64), dtype=torch.uint8, device=device)
+
+    def launch(self, trace=None):
+        check(lib().myr_mega_launch(_p(self.blob), self.n_ops, _p(self.workspace), ctypes.c_size_t(self.workspace.numel()),
+                                    self.n_counters, _p(trace), _stream()), "myr_mega_launch")
+
+
 def _i64(v):
     return ctypes.c_int64(v)
 

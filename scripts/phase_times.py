@@ -38,3 +38,33 @@ for _ in range(32):
 e1 = ev()
 torch.cuda.synchronize()
 print("graph replay only: %.3f ms/step (%d kernel nodes)" % (e0.elapsed_time(e1) / 32, st.graph_nodes))
+# op-chain trace of the persistent decode kernel (globaltimer, ns)
+if st.mega is not None:
+    n_ops, G = st.mega.n_ops, 148
+    tr = torch.zeros(3 * n_ops + n_ops * G * 2 + n_ops * 8, dtype=torch.int64, device=dev)
+    st.mega.launch(trace=tr)
+    torch.cuda.synchronize()
+    tc = tr.cpu()
+    t = tc[:3 * n_ops].reshape(-1, 3)
+    per = tc[3 * n_ops:3 * n_ops + n_ops * G * 2].reshape(n_ops, G, 2)
+    fine = tc[3 * n_ops + n_ops * G * 2:].reshape(n_ops, 8)
+    t0 = int(t[0, 0])
+    names = ["embed"] + ["qkv", "attn", "o", "gu", "down"] * dims.llama.layers + ["lm_head"]
+    prev = t0
+    agg = {}
+    for i in range(n_ops):
+        done = int(t[i, 0])
+        if 6 <= i < 16:
+            d = per[i, :, 0]; s_ = per[i, :, 1]
+            d = d[d > 0]; s_ = s_[s_ > 0]
+            line = "op %3d %-7s done +%7.2f (dur %6.2f)" % (i, names[i], (done - t0) / 1e3, (done - prev) / 1e3)
+            if len(d):
+                line += " | last drain per CTA: min +%7.2f med +%7.2f max +%7.2f" % ((int(d.min()) - t0) / 1e3, (int(d.median()) - t0) / 1e3, (int(d.max()) - t0) / 1e3)
+            if len(s_):
+                line += " | saw input: min +%7.2f max +%7.2f" % ((int(s_.min()) - t0) / 1e3, (int(s_.max()) - t0) / 1e3)
+            print(line)
+            if names[i] in ('o', 'down'):
+                print('      closer: ' + ' '.join('%s+%.2f' % (nm, (int(fine[i, k]) - t0) / 1e3) for k, nm in enumerate(['sum', 'stored', 'fenced', 'elected', 'tail', 'pass1', 'normed', 'flag'])))
+        agg.setdefault(names[i], []).append((done - prev) / 1e3)
+        prev = done
+    print({k: round(sum(v) / len(v), 2) for k, v in agg.items()}, "total %.1f us" % ((prev - t0) / 1e3))

@@ -154,3 +154,35 @@ def test_vit_full_width_two_blocks_vs_oracle(O):
     e = _err(x, O.vit_forward(sd, image, d.vit))
     print("vit full width (1408, dh=88, 257 tokens), 2 blocks: rel err %.2e" % e)
     assert e < TOL_ACT
+
+
+@pytest.mark.parametrize("lora_r", [0, 8])
+def test_persistent_decode_step_matches_multi_kernel_step(lora_r):
+    """decode_mega.cu (one persistent launch per decode step) against the multi-kernel step it replaces: same weights,
+    same cache, same state -> logits within fp16 accumulation-order noise, tokens identical, state left clean for replays."""
+    from myriad_b200 import kernels as K
+    d = syn.mid_dims(lora_r=lora_r, llama_layers=2)
+    sd = syn.make_state_dict(d, 1)
+    eng = _engine(d, sd)
+    torch.manual_seed(0)
+    B, S = 3, 21
+    x = (torch.randn(B, S, d.llama.hidden) * 0.5).cuda()
+    stops = ((100000,),)
+    eng.use_mega = False
+    t_multi = eng.greedy_decode(x.clone(), 12, stops)
+    st = list(eng._decode_graphs.values())[0]
+    logits_multi = st.logits.clone()
+    eng._decode_graphs = {}
+    eng.use_mega = True
+    t_mega = eng.greedy_decode(x.clone(), 12, stops)
+    st = list(eng._decode_graphs.values())[0]
+    assert st.mega is not None, "the persistent decode kernel must be the path taken"
+    e = _err(st.logits, logits_multi)
+    print("persistent decode step (lora_r=%d): last-step logits rel diff vs multi-kernel %.2e; tokens %s" % (lora_r, e, t_mega.tolist()))
+    assert t_mega.tolist() == t_multi.tolist()
+    assert e < 2e-3
+    ws = st.mega.workspace.view(torch.int32)
+    n_int = 2 * st.mega.n_ops + st.mega.n_counters
+    assert int(ws[:n_int].abs().sum()) == 0, "flags / counters must be left at zero"
+    t_again = eng.greedy_decode(x.clone(), 12, stops)
+    assert t_again.tolist() == t_mega.tolist(), "replays must be reproducible"
