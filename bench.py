@@ -154,6 +154,9 @@ def run_ours(args):
 
     value = world * BATCH * args.steps / (ms / 1e3)
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
+    train = None
+    if not args.no_train:
+        train = run_train_leg(args, dims, dev, world, rank, barrier)
     peaks = _peaks()
     extra = {}
     roof = None
@@ -162,6 +165,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import CpuSample
+        torch.set_num_threads(os.cpu_count() or 1)
         cs = CpuSample()
         v, parts = cs.run(NEW_TOKENS)
         cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": cs.describe(NEW_TOKENS),
@@ -179,11 +183,67 @@ def run_ours(args):
                     "d2h_bytes_per_step": BATCH * NEW_TOKENS * 4 + 8 * NEW_TOKENS, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "new_tokens_per_s": ntok / (ms / 1e3) * world, "weights_load_s": round(t_load, 1),
+            "train": train,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_train_leg(args, dims, dev, world, rank, barrier):
+    """Second half of BASELINE.json's metric: train tokens/s. One step = Myriad.forward + backward + gradient all-reduce
+    (NCCL, flat fp32 buffer of the trainable parameters) + fused AdamW on an MVTec-shaped batch per GPU (batch_size_train 4:
+    2 normal + 2 augmented samples, runner_base.py:546-549; stage 1 = VEInstructor + VETokenizer both on the gradient path;
+    LoRA r = 8 of loraadapter_simple_myriad_finetune.yaml). tokens = LLM sequence positions processed (B x L)."""
+    import torch
+    import torch.distributed as dist
+
+    from myriad_b200 import synthetic as syn
+    try:
+        from myriad_b200.training import MyriadTrainer
+        tr = MyriadTrainer(syn.LazyStateDict(dims, seed=0, device=dev), dims, device=dev, max_batch=BATCH, max_seq=256)
+        image, maps = syn.make_inputs(BATCH, seed=4321 + rank, device="cpu")
+        image_h, maps_h = image.pin_memory(), maps.pin_memory()
+        ids_b, ids_a = syn.make_prompt_ids(dims.llama.vocab)
+        g = torch.Generator().manual_seed(99 + rank)
+        Lt = 32
+        text = torch.randint(3, dims.llama.vocab, (BATCH, Lt), generator=g)
+        tmask = torch.ones(BATCH, Lt, dtype=torch.long)
+        text[:, 16:] = dims.llama.eos  # 16 answer tokens, right-padded with eos (= pad, myriad.py:182) to 32
+        tmask[:, 16:] = 0
+
+        def step():
+            im, mp = image_h.to(dev, non_blocking=True), maps_h.to(dev, non_blocking=True)
+            return tr.train_step(im, mp, 1, ids_b, ids_a, text, tmask)
+
+        for _ in range(max(args.warmup, 3)):
+            loss = step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = max(1, args.steps)
+        e0.record()
+        for _ in range(n):
+            loss = step()
+        loss_v = float(loss.item())  # device -> host read of the step's result inside the timed region
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        L = 1 + 6 + tr.num_image_tokens(1) + 26 + Lt
+        out = {"metric": "train tokens/sec", "value": world * BATCH * L * n / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms / n,
+               "images_per_s": world * BATCH * n / (ms / 1e3), "loss": loss_v,
+               "config": {"workload": "myriad_stage2_lora_finetune_b4", "batch_per_gpu": BATCH, "seq_len": L, "stage": 1, "lora_r": 8,
+                          "trainable_params": int(tr.flat_params.numel()), "allreduce_bytes_per_step": int(tr.flat_grads.numel()) * 4 if world > 1 else 0,
+                          "optimizer": "fused AdamW (flat fp32 buffer)", "includes": "h2d of the batch, fwd, bwd, all-reduce, AdamW, loss d2h"}}
+        del tr
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:  # the inference line must still be printed
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
 
 def roofline_probe(eng, dims, dev, peaks):
@@ -259,6 +319,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle.cpu_baseline import CpuSample
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core
     cs = CpuSample()
     vals = []
     steps = max(1, min(args.steps, 3))
@@ -286,6 +347,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train tokens/s)")
     ap.add_argument("--profile", action="store_true", help="minimal run for ncu (numbers printed under a profiler are not bench values)")
     args = ap.parse_args()
     if args.impl == "reference":

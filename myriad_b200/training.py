@@ -590,14 +590,12 @@ class MyriadTrainer(MyriadEngine):
     def optimizer_step(self, lr=None):
         """DDP gradient averaging (runner_base.py:96-98: one all-reduce of the flat buffer over NCCL/NVLink) + fused AdamW
         (runner_base.py:105-139) + refresh of the fp16 operand copies."""
-        import torch.distributed as dist
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        if world > 1:
-            dist.all_reduce(self.flat_grads)
+        from .dp import allreduce_flat_grads
+        mean_scale = allreduce_flat_grads(self.flat_grads)  # sum over ranks; 1 / world folded into the optimizer's unscale
         self.opt_step += 1
         hp = self.hp
         K.adamw_step(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.wd_mask, hp["lr"] if lr is None else lr,
-                     hp["beta1"], hp["beta2"], hp["eps"], hp["wd"], self.opt_step, inv_scale=1.0 / world, found_inf=self.found_inf)
+                     hp["beta1"], hp["beta2"], hp["eps"], hp["wd"], self.opt_step, inv_scale=mean_scale, found_inf=self.found_inf)
         self.refresh_trainables()
 
     def train_step(self, image, maps, stage, ids_before, ids_after, text_ids, text_mask, lr=None):

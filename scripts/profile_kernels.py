@@ -1,10 +1,12 @@
 """Small driver for `ncu --set full` captures of the hot kernels in their bench configurations (run under gpurun):
-   ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 8 -o gpurun_out/prof_gemm python scripts/profile_kernels.py
+   ncu --set full --clock-control none --import-source on -k regex:gemm_tc -c 12 -o gpurun_out/prof_gemm python scripts/profile_kernels.py
 """
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import math
+
 import torch
 
 from myriad_b200 import kernels as K
@@ -12,28 +14,57 @@ from myriad_b200 import kernels as K
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 B = 4
-# decode weight-streaming GEMMs (T = 4): gate_up and down of LLaMA-7B, distinct weights per launch (no L2 reuse)
+# decode weight-streaming GEMMs (T = 4) in layer order: qkv (+LoRA A rows), o (+res), gate/up (+SwiGLU), down (+res);
+# fresh weights per launch (no L2 reuse)
 x = torch.randn(B, 4096, device=dev).half()
 a = torch.randn(B, 11008, device=dev).half()
 res = torch.zeros(B, 4096, device=dev)
-for i in range(3):
+qkv = torch.empty(B, 12304, device=dev, dtype=torch.float16)
+act = torch.empty(B, 11008, device=dev, dtype=torch.float16)
+for i in range(2):
+    wq = (torch.randn(12304, 4096, device=dev) * 0.02).half()
+    wo = (torch.randn(4096, 4096, device=dev) * 0.02).half()
     wgu = (torch.randn(22016, 4096, device=dev) * 0.02).half()
     wd = (torch.randn(4096, 11008, device=dev) * 0.02).half()
-    K.gemm(x, wgu)
-    K.gemm(a, wd, res=res, out=res)
-# ViT GEMMs at the bench batch (T = 4 * 257)
+    K.gemm(x, wq, out=qkv, w_static=True)
+    K.gemm(x, wo, res=res, out=res, w_static=True)
+    K.gemm(x, wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
+    K.gemm(a, wd, res=res, out=res, w_static=True)
+# ViT GEMMs at the bench batch (T = 4 * 257): qkv, fc1 + GELU, fc2 + residual
 T = B * 257
 h = torch.randn(T, 1408, device=dev).half()
 w1 = (torch.randn(6144, 1408, device=dev) * 0.02).half()
 b1 = torch.zeros(6144, device=dev).half()
-for i in range(2):
-    K.gemm(h, w1, bias=b1, act=K.ACT_GELU)
-# ViT attention (dh = 88, N = 257) and LLaMA prefill attention (dh = 128, S = 131, causal)
+w2 = (torch.randn(1408, 6144, device=dev) * 0.02).half()
+b2 = torch.zeros(1408, device=dev).half()
+xr = torch.zeros(T, 1408, device=dev)
+m = K.gemm(h, w1, bias=b1, act=K.ACT_GELU)
+K.gemm(m, w2, bias=b2, res=xr, out=xr)
+# LLaMA prefill GEMM (T = 524): gate/up + SwiGLU
+hp = torch.randn(524, 4096, device=dev).half()
+K.gemm(hp, wgu, act=K.ACT_SWIGLU)
+# ViT attention (dh = 88, N = 257), LLaMA prefill attention (dh = 128, S = 131, causal)
 D = 1408
 qkv = torch.randn(T, 3 * D, device=dev).half()
 out = torch.empty(T, D, device=dev, dtype=torch.float16)
 s = (3 * D, 257 * 3 * D, 88)
 for i in range(2):
     K.attention(qkv, qkv[:, D:], qkv[:, 2 * D:], out, B, 16, 257, 257, 88, 1.0, s, s, s, (D, 257 * D, 88))
+S, Dl = 131, 4096
+ql = torch.randn(B * S, 3 * Dl, device=dev).half()
+ol = torch.empty(B * S, Dl, device=dev, dtype=torch.float16)
+sl = (3 * Dl, S * 3 * Dl, 128)
+K.attention(ql, ql[:, Dl:], ql[:, 2 * Dl:], ol, B, 32, S, S, 128, 1 / math.sqrt(128), sl, sl, sl, (Dl, S * Dl, 128), causal=True)
+# decode attention (one launch per layer and step): 4 sequences, 32 heads, 160 cached tokens
+kc = torch.randn(B, 256, Dl, device=dev).half()
+vc = torch.randn(B, 256, Dl, device=dev).half()
+qd = torch.randn(B, 3 * Dl + 16, device=dev).half()
+pos = torch.full((B,), 160, dtype=torch.int32, device=dev)
+kvl = torch.full((B,), 161, dtype=torch.int32, device=dev)
+cos = torch.randn(2048, 64, device=dev)
+od = torch.empty(B, Dl, device=dev, dtype=torch.float16)
+bq = torch.randn(Dl, 8, device=dev).half()
+for i in range(2):
+    K.decode_attention(qd, B, 32, 128, pos, cos, cos, kc, vc, kvl, od, 1 / math.sqrt(128), cache_off=160, lora=(bq, bq, 8, 2.0))
 torch.cuda.synchronize()
 print("done")
