@@ -85,18 +85,6 @@ __device__ __forceinline__ long long gtime() {
 __device__ __forceinline__ void mg_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(MG_EPI_THREADS) : "memory"); }
 __device__ __forceinline__ void mg_attn_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // spin until sync[i] >= target (watchdog: a protocol bug traps instead of hanging the GPU)
 __device__ __forceinline__ void wait_dep(const int* flags, int i, int target) {
   if (i < 0) return;

@@ -77,6 +77,7 @@ struct GemmKernelParams {
   long long o_bs0, o_bs1;          // output element strides of the two batch dims
   int w_static;
   int tmem_cols, acc_stride;       // TMEM columns allocated by this CTA, columns between the two accumulator stages
+  int n_mp;                        // cluster mode: pairs of token tiles (a "tile" index then names a pair x one weight tile)
   Epilogue ep;
 };
 
@@ -233,6 +234,20 @@ __device__ __forceinline__ Seg next_seg(long long& g, long long g1, int kb_total
 struct TileCoord {
   int m0, n0, b0, b1, bidx;
 };
+// cluster of 2 CTAs: both work on the same weight (B) tile and on adjacent token tiles; each loads half of the B tile
+// and multicasts it to the pair, halving the L2 -> SM traffic that bounds the lanes = tokens arrangement
+__device__ __forceinline__ TileCoord tile_coord_pair(const GemmKernelParams& p, int tile, int rank) {
+  TileCoord c;
+  const int nt = tile / p.n_mp;
+  const int mp = tile - nt * p.n_mp;
+  c.bidx = 0;
+  c.b0 = 0;
+  c.b1 = 0;
+  c.m0 = (2 * mp + rank) * BM;
+  c.n0 = nt * p.BN;
+  return c;
+}
+
 __device__ __forceinline__ TileCoord tile_coord(const GemmKernelParams& p, int tile) {
   TileCoord c;
   const int per_batch = p.n_mt * p.n_nt;
@@ -255,7 +270,7 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmKernelParams& p, int t
 
 // kOcc = 2 (weight streaming): <= 96 registers, <= ~110 KB smem and only the TMEM columns it needs, so the CTA of the NEXT
 // GEMM in the stream (programmatic dependent launch) is resident and has its weight ring full before this one drains.
-template <int kOcc>
+template <int kOcc, int kCluster = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, kOcc)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKernelParams p) {
@@ -275,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], kCluster);  // cluster mode: a stage is free once BOTH CTAs' MMAs have read it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -290,11 +305,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
+  const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
+  const int unit = kCluster > 1 ? (int)(blockIdx.x / kCluster) : (int)blockIdx.x;  // both CTAs of a cluster walk the same range
 
-  const long long g0 = (long long)blockIdx.x * p.per;
+  const long long g0 = (long long)unit * p.per;
   const long long g1 = (g0 + p.per < p.total_kb) ? g0 + p.per : p.total_kb;
   const uint32_t b_bytes = (uint32_t)p.BN * BK * 2;
   const uint32_t tx_bytes = A_STAGE_BYTES + b_bytes;
@@ -325,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       long long g = g0;
       while (g < g1) {
         const Seg s = next_seg(g, g1, p.kb_total);
-        const TileCoord c = tile_coord(p, s.tile);
+        const TileCoord c = kCluster > 1 ? tile_coord_pair(p, s.tile, crank) : tile_coord(p, s.tile);
         for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
           uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -342,7 +360,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(sa + 8192, &tmA, &full[stage], c.m0 + 64, kb * BK, c.b1, c.b0);
             }
           }
-          if (!p.b_mn) {
+          if constexpr (kCluster > 1) {
+            // my half of the weight tile, delivered to both CTAs of the pair
+            const int half_rows = p.BN / 2;
+            tma_load_4d_multicast(sb + crank * half_rows * (BK * 2), &tmB, &full[stage], kb * BK, c.n0 + crank * half_rows, 0, 0,
+                                  (uint16_t)0x3);
+          } else if (!p.b_mn) {
             tma_load_4d(sb, &tmB, &full[stage], kb * BK, c.n0, c.b1, c.b0);
           } else {
             for (int i = 0; i < p.BN / 64; ++i) tma_load_4d(sb + i * 8192, &tmB, &full[stage], c.n0 + 64 * i, kb * BK, c.b1, c.b0);
@@ -380,7 +403,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db = make_smem_desc(sb + kk * b_kstep, b_lbo, 1024);
             tc_mma_f16(d_tmem, da, db, p.idesc, (kb > s.kb0 || kk > 0) ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
+          if constexpr (kCluster > 1)
+            tc_commit_multicast(&empty[stage], (uint16_t)0x3);  // the peer multicasts into this stage too
+          else
+            tc_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -406,16 +432,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     long long g = g0;
     while (g < g1) {
       const Seg s = next_seg(g, g1, p.kb_total);
-      const TileCoord c = tile_coord(p, s.tile);
+      const TileCoord c = kCluster > 1 ? tile_coord_pair(p, s.tile, crank) : tile_coord(p, s.tile);
       const long long boff = (long long)c.b0 * p.o_bs0 + (long long)c.b1 * p.o_bs1;
       // which CTAs cover this tile
       const long long tb = (long long)s.tile * p.kb_total;
       const int first = (int)(tb / p.per), last = (int)((tb + p.kb_total - 1) / p.per);
       const int n_seg = last - first + 1;
-      const int seg = (int)blockIdx.x - first;
+      const int seg = unit - first;
       const bool via_ws = n_seg > 1 || (swiglu && !p.row_mode);
       const int nchunks = p.BN / 16;
       float* ws = p.partial + ((size_t)s.tile * p.max_seg + seg) * ((size_t)p.BN * BM);
+
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
@@ -588,6 +615,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();  // the peer may still multicast into / signal this CTA's shared memory
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -596,6 +624,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------
 struct Plan {
   int row_mode, BN, n_mt, n_nt, kb_total, per, grid, max_seg, num_stages, stage_bytes;
+  int cluster, n_mp;  // cluster = 2: CTA pairs share a multicast weight tile (tiles are then (token-tile pair, weight tile))
   long long total_kb;
   int n_tiles;
 };
@@ -609,10 +638,24 @@ static Plan make_plan(const myr_gemm_args* a, int nbatch, bool allow_split, size
   const bool swiglu = a->act == MYR_ACT_SWIGLU;
   pl.kb_total = ceil_div(K, BK);
   pl.row_mode = (T > 64) ? 1 : 0;
+  pl.cluster = 1;
+  pl.n_mp = 0;
   int gran;
   if (pl.row_mode) {
     gran = swiglu ? 128 : (a->w_mn_major ? 64 : 16);
     pl.n_mt = ceil_div(T, BM);
+    static int cluster_env = -1;
+    if (cluster_env < 0) {
+      const char* e = getenv("MYR_GEMM_CLUSTER");
+      cluster_env = (e && e[0] == '0') ? 0 : 1;
+    }
+    // lanes = tokens is bounded by L2 -> SM bandwidth (~42 B/clk/SM): pairs of CTAs on adjacent token tiles share the
+    // weight tile through TMA multicast, which halves the weight traffic per CTA
+    // (measured on B200: +30 % at T = 8224, F = 6144, K = 1408; a loss below ~32 token tiles, where pairing costs a wave)
+    if (cluster_env && !a->x_mn_major && !a->w_mn_major && nbatch == 1 && pl.n_mt >= 32 && a->ksplit_hint <= 1 && sms % 2 == 0)
+      pl.cluster = 2;
+    const int m_units = pl.cluster == 2 ? ceil_div(pl.n_mt, 2) : pl.n_mt;
+    const int slots = pl.cluster == 2 ? sms / 2 : sms;
     int best_bn = 0;
     if (a->bn_hint > 0) {
       best_bn = round_up(a->bn_hint, gran);
@@ -623,10 +666,14 @@ static Plan make_plan(const myr_gemm_args* a, int nbatch, bool allow_split, size
       const int f_cap = round_up(F, gran);
       for (int bn = 256; bn >= (gran > 32 ? gran : 32); bn -= gran) {
         if (bn > f_cap && bn != gran) continue;
-        const long long tiles = (long long)pl.n_mt * ceil_div(F, bn) * nbatch;
-        const long long rounds = (tiles + sms - 1) / sms;
-        const double per = (bn / 2.0 > 32 + bn / 4.0) ? bn / 2.0 : 32 + bn / 4.0;
-        const double cost = rounds * (pl.kb_total * 4 * per + 400.0 + 3.0 * bn);
+        const long long tiles = (long long)m_units * ceil_div(F, bn) * nbatch;
+        const long long rounds = (tiles + slots - 1) / slots;
+        // cycles per 64-wide k-block: tensor pipe 2 * bn; L2 -> SM operand traffic at ~36 B/clk/SM (the binding one for
+        // bn <= 256: measured 12 TB/s chip-wide on the T = 524 gate/up GEMM); multicast halves the weight-tile bytes
+        const double mma = 2.0 * bn;
+        const double l2 = (16384.0 + 128.0 * bn / pl.cluster) / 36.0;
+        const double per = mma > l2 ? mma : l2;
+        const double cost = rounds * (pl.kb_total * per + 400.0 + 3.0 * bn);
         if (cost < best - 1e-9) {
           best = cost;
           best_bn = bn;
@@ -644,16 +691,22 @@ static Plan make_plan(const myr_gemm_args* a, int nbatch, bool allow_split, size
     pl.n_nt = ceil_div(T, pl.BN);
   }
   pl.n_tiles = pl.n_mt * pl.n_nt * nbatch;
+  if (pl.cluster == 2) {
+    pl.n_mp = ceil_div(pl.n_mt, 2);
+    pl.n_tiles = pl.n_mp * pl.n_nt;
+  }
   pl.total_kb = (long long)pl.n_tiles * pl.kb_total;
   pl.stage_bytes = A_STAGE_BYTES + pl.BN * BK * 2;
   int st = (pl.row_mode ? SMEM_TILE_BUDGET : SMEM_TILE_BUDGET_OCC2) / pl.stage_bytes;
   pl.num_stages = st > MAX_STAGES ? MAX_STAGES : st;
 
-  // data-parallel default: whole tiles per CTA
-  const int tiles_per_cta = ceil_div(pl.n_tiles, sms);
+  // data-parallel default: whole tiles per CTA (per CTA pair in cluster mode)
+  const int units = pl.cluster == 2 ? sms / 2 : sms;
+  const int tiles_per_cta = ceil_div(pl.n_tiles, units);
   pl.per = tiles_per_cta * pl.kb_total;
-  pl.grid = ceil_div(pl.n_tiles, tiles_per_cta);
+  pl.grid = ceil_div(pl.n_tiles, tiles_per_cta) * pl.cluster;
   pl.max_seg = 1;
+  if (pl.cluster == 2) return pl;
   bool want_split = false;
   int per = pl.per;
   if (a->ksplit_hint > 1) {
@@ -764,7 +817,7 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
     int rc = make_tmap_f16(&tmA, pa, 4, dims, strides, box);
     if (rc) return rc;
     if (!b_mn) {
-      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)rows_b; box[0] = BK; box[1] = (uint32_t)pl.BN;
+      dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)rows_b; box[0] = BK; box[1] = (uint32_t)(pl.BN / pl.cluster);
     } else {
       dims[0] = (uint64_t)rows_b; dims[1] = (uint64_t)a->K; box[0] = 64; box[1] = BK;
     }
@@ -785,6 +838,7 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   p.idesc = make_idesc_f16(BM, pl.BN, a_mn, b_mn);
   p.partial = partial; p.counters = counters;
   p.nb1 = nb1; p.nbatch = nbatch; p.o_bs0 = a->o_bs0; p.o_bs1 = a->o_bs1;
+  p.n_mp = pl.n_mp;
   // weights may be prefetched ahead of the dependency only when they are the K-major A operand and the caller says so
   p.w_static = (a->w_static && !pl.row_mode && !a_mn) ? 1 : 0;
   if (pl.row_mode) {
@@ -816,10 +870,14 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   static bool attr_set = false;
   if (!attr_set) {
     MYR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     MYR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr_set = true;
   }
-  if (pl.row_mode)
+  if (pl.cluster == 2)
+    MYR_CHECK_CUDA(launch_kernel_cluster(gemm_tc_kernel<1, 2>, dim3((unsigned)pl.grid), dim3(GEMM_THREADS), smem_bytes, stream,
+                                         a->pdl != 0, 2, tmA, tmB, p));
+  else if (pl.row_mode)
     MYR_CHECK_CUDA(launch_kernel(gemm_tc_kernel<1>, dim3((unsigned)pl.grid), dim3(GEMM_THREADS), smem_bytes, stream, a->pdl != 0,
                                  tmA, tmB, p));
   else
