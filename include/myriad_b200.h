@@ -86,6 +86,9 @@ typedef struct {
 } myr_gemm_args;
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);
 int myr_gemm_f16(const myr_gemm_args* args, void* stream);
+/* Profiling aid: while set, every GEMM launch writes 148 x 6 %globaltimer stamps (CTA start, predecessor released, last MMA
+ * issued, last accumulator ready, epilogue done, -) at `buf` and advances `buf` by that much; NULL stops tracing. */
+void myr_gemm_set_trace(void* buf);
 /* Programmatic dependent launch on/off for the whole library (default on; env MYR_PDL=0 disables). */
 void myr_set_pdl(int32_t enabled);
 
@@ -164,6 +167,8 @@ typedef struct {
   const void* lora_bq; const void* lora_bv; int32_t lora_r; float lora_scale;
   float scale;
   void* out; int64_t ldo;                /* fp16 [B, H * dh] */
+  int64_t next_layer_stride;             /* elements between this layer's and the next layer's cache (0 = last layer): the
+                                            kernel prefetches the next layer's slice into L2 */
 } myr_decode_attn_args;
 int myr_decode_attention(const myr_decode_attn_args* args, void* stream);
 

@@ -46,6 +46,7 @@ extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_
   p.lora_r = (a->lora_bq && a->lora_bv) ? a->lora_r : 0; p.lora_scale = a->lora_scale;
   p.scale = a->scale;
   p.out = reinterpret_cast<__half*>(a->out); p.ldo = a->ldo;
+  p.next_layer_stride = a->next_layer_stride;
   MYR_CHECK_CUDA(launch_kernel(decode_attn_kernel, dim3(a->H, a->B), dim3(DA_THREADS), (size_t)a->cache_len * sizeof(float), stream,
                                true, p));
   MYR_CHECK_LAUNCH();

@@ -20,6 +20,7 @@ struct DecodeAttnParams {
   const __half* lora_bq; const __half* lora_bv; int lora_r; float lora_scale;
   float scale;
   __half* out; long long ldo;        // [B, H * dh]
+  long long next_layer_stride;       // elements from this layer's cache to the next layer's (0: none): L2 prefetch hint
 };
 
 __device__ __forceinline__ void da_unpack8(const uint4& u, float (&f)[8]) {
@@ -168,6 +169,18 @@ __device__ __forceinline__ void decode_attn_task(const DecodeAttnParams& p, int 
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) s_acc[warp][lane * 4 + i] = acc[i];
+  if (p.next_layer_stride) {
+    // The next layer's attention reads the same (head, row) slice of ITS cache ~100 us from now. At decode the cache is
+    // touched once per step, so those lines sit in DRAM and, under the weight stream, a miss costs microseconds of a
+    // latency-bound kernel: ask L2 for them now (weights are loaded evict-first, so the lines survive until then).
+    const __half* kn = kbase + p.next_layer_stride;
+    const __half* vn = vbase + p.next_layer_stride;
+    for (int j = tid; j < 2 * kvl; j += DA_THREADS) {  // one 128-byte line = half a K or V row
+      const size_t o = (size_t)(j >> 1) * p.c_ts + (j & 1) * 64;
+      prefetch_l2(kn + o);
+      prefetch_l2(vn + o);
+    }
+  }
   sync();
   {
     const float o = (s_acc[0][tid] + s_acc[1][tid]) + (s_acc[2][tid] + s_acc[3][tid]);

@@ -78,9 +78,15 @@ struct GemmKernelParams {
   int w_static;
   int tmem_cols, acc_stride;       // TMEM columns allocated by this CTA, columns between the two accumulator stages
   int n_mp;                        // cluster mode: pairs of token tiles (a "tile" index then names a pair x one weight tile)
+  long long* trace;                // debug (MYR_GEMM_TRACE): per CTA 6 x %globaltimer ns, see myr_gemm_trace_read
   Epilogue ep;
 };
 
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // erf with |abs error| <= 1.5e-7 (Abramowitz-Stegun 7.1.26): well below the fp16 rounding applied to every GELU output.
@@ -309,6 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 6 + 0] = gtime_ns();
   const int crank = kCluster > 1 ? (int)cluster_ctarank() : 0;
   const int unit = kCluster > 1 ? (int)(blockIdx.x / kCluster) : (int)blockIdx.x;  // both CTAs of a cluster walk the same range
 
@@ -339,6 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       pdl_wait();
+      if (p.trace) p.trace[blockIdx.x * 6 + 1] = gtime_ns();
       int it = 0;
       long long g = g0;
       while (g < g1) {
@@ -413,6 +421,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc_commit(&tfull[as]);  // accumulator complete -> epilogue
+        if (p.trace) p.trace[blockIdx.x * 6 + 2] = gtime_ns();  // last MMA of the segment issued
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -446,6 +455,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      if (p.trace && epi_tid == 0) p.trace[blockIdx.x * 6 + 3] = gtime_ns();  // accumulator of the (last) segment ready
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * p.acc_stride;
 
       if (via_ws) {
@@ -613,6 +623,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (p.trace && threadIdx.x == 64) p.trace[blockIdx.x * 6 + 4] = gtime_ns();  // epilogue / fix-up of this CTA done
   tc_fence_before();
   __syncthreads();
   if constexpr (kCluster > 1) cluster_sync_all();  // the peer may still multicast into / signal this CTA's shared memory
@@ -747,6 +758,10 @@ static Plan make_plan(const myr_gemm_args* a, int nbatch, bool allow_split, size
 
 using namespace myr;
 
+static void* g_gemm_trace = nullptr;
+/* debug: every following GEMM launch writes 148 x 6 timestamps at `buf` and advances it (NULL stops tracing) */
+extern "C" void myr_gemm_set_trace(void* buf) { g_gemm_trace = buf; }
+
 extern "C" size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K) {
   (void)K;
   // counters + partial tiles: a split tile keeps at most ceil(kb / per) + 1 <= 4 partials in the shapes the heuristics pick
@@ -839,6 +854,8 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   p.partial = partial; p.counters = counters;
   p.nb1 = nb1; p.nbatch = nbatch; p.o_bs0 = a->o_bs0; p.o_bs1 = a->o_bs1;
   p.n_mp = pl.n_mp;
+  p.trace = reinterpret_cast<long long*>(g_gemm_trace);
+  if (g_gemm_trace) g_gemm_trace = reinterpret_cast<char*>(g_gemm_trace) + 148 * 6 * sizeof(long long);  // next launch, next slot
   // weights may be prefetched ahead of the dependency only when they are the K-major A operand and the caller says so
   p.w_static = (a->w_static && !pl.row_mode && !a_mn) ? 1 : 0;
   if (pl.row_mode) {

@@ -344,8 +344,9 @@ class MyriadEngine:
         lora = (L.lora.bq, L.lora.bv, self.d.lora_r, L.lora.scale) if L.lora is not None else None  # myriad.py:171-178
         if S == 1 and dh == 128 and kv_len is not None:
             # decode: rotary + LoRA-B + cache append + attention over the cache in one CUDA-core launch
+            nxt = self.kcache.stride(0) if li + 1 < l.layers else 0
             K.decode_attention(qkv, B, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, kv_len, ctx, 1.0 / math.sqrt(dh),
-                               cache_off=cache_off, cache_off_dev=cache_off_dev, lora=lora)
+                               cache_off=cache_off, cache_off_dev=cache_off_dev, lora=lora, next_layer_stride=nxt)
         else:
             K.rope_cache(qkv, B, S, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, cache_off=cache_off,
                          cache_off_dev=cache_off_dev, lora=lora)

@@ -228,10 +228,12 @@ class DecodeAttnArgs(ctypes.Structure):
         ("lora_bq", ctypes.c_void_p), ("lora_bv", ctypes.c_void_p), ("lora_r", ctypes.c_int32), ("lora_scale", ctypes.c_float),
         ("scale", ctypes.c_float),
         ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64),
+        ("next_layer_stride", ctypes.c_int64),
     ]
 
 
-def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, scale, cache_off=0, cache_off_dev=None, lora=None):
+def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, scale, cache_off=0, cache_off_dev=None, lora=None,
+                     next_layer_stride=0):
     """One new token per sequence: LoRA-B + RoPE + KV-cache append + attention over the cache in one launch."""
     a = DecodeAttnArgs()
     a.qkv, a.ldq = qkv.data_ptr(), qkv.stride(0)
@@ -248,6 +250,7 @@ def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, 
         a.lora_bq, a.lora_bv, a.lora_r, a.lora_scale = bq.data_ptr(), bv.data_ptr(), r, s
     a.scale = scale
     a.out, a.ldo = out.data_ptr(), out.stride(0)
+    a.next_layer_stride = next_layer_stride
     check(lib().myr_decode_attention(ctypes.byref(a), _stream()), "myr_decode_attention")
     return out
 
