@@ -84,7 +84,8 @@ class MyriadTrainer(MyriadEngine):
                 t = t.permute(0, 2, 3, 1)
             self.flat_params[o:o + _numel(shape)].copy_(t.reshape(-1))
             # runner_base.py:115: no weight decay for ndim < 2 or bias / ln / bn parameters
-            if len(shape) >= 2 and "bias" not in key:
+            from .optim import no_weight_decay
+            if not no_weight_decay(key, len(shape)):
                 self.wd_mask[o:o + _numel(shape)] = 1
         self.instw = self._conv_views("VEInstructor", 1) if d.use_instructor else None
         self.tokw = self._conv_views("VETokenizer", 5) if d.use_tokenizer else None
@@ -179,6 +180,28 @@ class MyriadTrainer(MyriadEngine):
             t = self.param(key)
             out[key] = (t.permute(0, 3, 1, 2) if kind == "conv" else t).contiguous().clone()
         return out
+
+    def export_flat(self, buf):
+        """{reference key: tensor in the reference layout} view of any flat buffer shaped like flat_params."""
+        out = {}
+        for key in self.segments:
+            t = self.param(key, buf)
+            out[key] = (t.permute(0, 3, 1, 2) if self.segments[key][2] == "conv" else t).contiguous().clone()
+        return out
+
+    def import_flat(self, buf, tensors):
+        for key, (off, shape, kind) in self.segments.items():
+            if key not in tensors:
+                continue
+            t = tensors[key].to(self.dev, F32)
+            if kind == "conv":
+                t = t.permute(0, 2, 3, 1)
+            buf[off:off + _numel(shape)].copy_(t.reshape(-1))
+
+    def import_state_dict(self, sd):
+        """Trainable parameters in the reference layout (a `ckpt:` file's "model" entry) -> flat buffer + fp16 operand copies."""
+        self.import_flat(self.flat_params, sd)
+        self.refresh_trainables()
 
     def export_grads(self, unscale=True):
         out = {}

@@ -300,3 +300,43 @@ def test_train_step_vs_live_oracle_and_update(O, golden):
         wd = 0.05 if (p.ndim >= 2 and "bias" not in k) else 0.0
         torch.optim.AdamW([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd).step()
         assert rel(after[k], p.data) < 1e-5, k
+
+
+def test_checkpoint_resume_and_lr_schedule(tmp_path):
+    """runner_base.py:592-672 semantics: save after N steps, resume in a fresh trainer, the next step lands on the same
+    parameters; the "model" entry holds exactly the trainable tensors in the reference's key names / layouts."""
+    from myriad_b200 import optim
+    from myriad_b200.training import MyriadTrainer
+    d = syn.mid_dims(lora_r=8)
+    sd = syn.make_state_dict(d, 4)
+    image, maps = syn.make_inputs(2, seed=5)
+    ids_b, ids_a = syn.make_prompt_ids(d.llama.vocab)
+    gen = torch.Generator().manual_seed(6)
+    text = torch.randint(3, d.llama.vocab, (2, 8), generator=gen)
+    tmask = torch.ones(2, 8, dtype=torch.long)
+    sched = optim.LinearWarmupCosineLR(max_epoch=1, iters_per_epoch=10, min_lr=1e-5, init_lr=1e-3, warmup_steps=2, warmup_start_lr=1e-4)
+    scaler = optim.DynamicLossScale(init_scale=1024.0)
+
+    def run(tr, steps, start):
+        for i in range(start, start + steps):
+            tr.train_step(image.cuda(), maps.cuda(), 1, ids_b, ids_a, text, tmask, lr=sched.lr(0, i))
+            scaler.update(bool(tr.found_inf.item()))
+
+    a = MyriadTrainer(sd, d, device="cuda:0", max_batch=2, max_seq=256)
+    run(a, 2, 0)
+    path = optim.save_checkpoint(a, str(tmp_path / "checkpoint_0.pth"), epoch=0, config={"run": {"init_lr": 1e-3}}, scaler=scaler)
+    run(a, 1, 2)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "config", "scaler", "epoch"}
+    assert ck["model"]["VETokenizer.meta_net.15.weight"].shape == (4096, 1024, 5, 5)
+    assert ck["model"]["llama_model.base_model.model.model.layers.0.self_attn.q_proj.lora_A.default.weight"].shape == (8, 4096)
+    assert not any(k.startswith(("visual_encoder", "Qformer", "llama_proj", "llama_model.model")) for k in ck["model"]), "frozen weights are not saved"
+    b = MyriadTrainer(sd, d, device="cuda:0", max_batch=2, max_seq=256)
+    sc2 = optim.DynamicLossScale()
+    assert optim.load_checkpoint(b, path, scaler=sc2) == 1 and b.opt_step == 2 and sc2.scale == scaler.scale
+    run(b, 1, 2)
+    pa, pb = a.export_state_dict(), b.export_state_dict()
+    worst = max(rel(pb[k], pa[k]) for k in pa)
+    moved = max(rel(pa[k], sd[k]) for k in pa)
+    print("resume: worst parameter difference after the resumed step %.2e (parameters moved %.2e from init)" % (worst, moved))
+    assert worst < 1e-5 and moved > 1e-4
