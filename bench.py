@@ -139,7 +139,10 @@ def run_ours(args):
 
     if args.profile:  # under ncu: one warm-up (graph capture), one step, nothing else
         step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()  # ncu --profile-from-start off: only the one step below is captured
         ms, ntok, launches = timed(step_resident, 1)
+        torch.cuda.profiler.stop()
         print(json.dumps({"profile_run": True, "ms_per_step_under_profiler": ms, "gpu_launches": launches}), flush=True)
         return
     for _ in range(max(args.warmup, 3)):
