@@ -83,7 +83,16 @@ typedef struct {
   int32_t alpha_set; float alpha; /* if alpha_set: v *= alpha (fp32, unrounded) after the activation, before the residual add */
   int32_t pdl;                 /* launch with programmatic stream serialization (overlaps the previous kernel's tail) */
   int32_t w_static;            /* w is not written by any kernel in flight: its tiles may be prefetched before the PDL wait */
+  /* Optional fused LlamaRMSNorm prologue (modeling_llama.py:66-74), small-batch path only (T <= 4, see below): when
+   * norm_h32 != NULL, x is ignored and the activations are rn_f16(h * rsqrt(mean(h^2) + norm_eps) * norm_gamma) computed from
+   * the fp32 rows norm_h32[t * norm_ldh + k] (k < K <= 4096) by every CTA itself. MYR_ERR_UNSUPPORTED if T > 4. */
+  const void* norm_h32; int64_t norm_ldh; const void* norm_gamma; float norm_eps;
 } myr_gemm_args;
+/* Small-batch path: T <= 4 with K-major fp16 operands, act NONE or SWIGLU and no scale_cols / round_acc / alpha / row
+ * groups / batch / hints runs on a CUDA-core weight-streaming kernel (csrc/gemv.cu: one CTA per SM owns whole output rows,
+ * no split tiles, no workspace). myr_set_gemv(0) (or env MYR_GEMV=0) routes those shapes to the tcgen05 kernel instead;
+ * returns the previous setting. */
+int32_t myr_set_gemv(int32_t enabled);
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);
 int myr_gemm_f16(const myr_gemm_args* args, void* stream);
 /* Profiling aid: while set, every GEMM launch writes 148 x 6 %globaltimer stamps (CTA start, predecessor released, last MMA

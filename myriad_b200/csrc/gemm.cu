@@ -769,6 +769,28 @@ extern "C" size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K) {
   return COUNTER_BYTES + tiles * 4 * 256 * BM * sizeof(float);
 }
 
+int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream);  // gemv.cu
+
+static int g_gemv = -1;  // < 0: not read from the environment yet
+static int gemv_enabled() {
+  if (g_gemv < 0) {
+    const char* e = getenv("MYR_GEMV");
+    g_gemv = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_gemv;
+}
+extern "C" int32_t myr_set_gemv(int32_t enabled) {
+  const int old = gemv_enabled();
+  g_gemv = enabled ? 1 : 0;
+  return old;
+}
+
+static bool gemv_eligible(const myr_gemm_args* a, int nbatch) {
+  return a->T <= 4 && !a->x_mn_major && !a->w_mn_major && nbatch == 1 && a->scale_cols == 0 && !a->round_acc && !a->alpha_set &&
+         a->out_group_rows == 0 && (a->act == MYR_ACT_NONE || a->act == MYR_ACT_SWIGLU) && a->K % 128 == 0 && a->bn_hint == 0 &&
+         a->ksplit_hint == 0;
+}
+
 extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MYR_CHECK_ARG(a != nullptr, "gemm: null args");
@@ -790,7 +812,14 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
                       !a->w_mn_major && a->scale_cols == 0,
                   "gemm: SwiGLU epilogue needs F %% 128 == 0 (64-row interleaved gate/up), fp16 out, no bias/residual");
   }
-  MYR_CHECK_ARG(a->T <= 64 || !a->x_mn_major || true, "gemm: unreachable");
+  if (gemv_enabled() && gemv_eligible(a, nbatch)) {
+    MYR_CHECK_ARG((a->res == nullptr || (a->ldr > 0)) && a->ldo > 0, "gemm: bad leading dimensions");
+    return myr_gemv_dispatch(a, stream);
+  }
+  if (a->norm_h32 != nullptr) {
+    set_error("gemm: the fused RMSNorm prologue exists on the small-batch path only (T <= 4, plain K-major operands, no hints)");
+    return MYR_ERR_UNSUPPORTED;
+  }
 
   size_t ws_floats = 0;
   int* counters = nullptr;

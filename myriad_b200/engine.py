@@ -34,6 +34,11 @@ class _Obj:
     pass
 
 
+def l_hidden_ok(dims):
+    """The fused RMSNorm prologue of csrc/gemv.cu holds one fp32 row slice per thread: hidden <= 4096, multiple of 8."""
+    return dims.llama.hidden <= 4096 and dims.llama.hidden % 8 == 0
+
+
 class MyriadEngine:
     # Inference layout of the LLaMA weights: LoRA A rows appended to the fused qkv weight (the rank-8 update is applied
     # inside the RoPE kernel) and gate/up rows interleaved in blocks of 64 for the fused SwiGLU GEMM epilogue. The trainer
@@ -54,6 +59,8 @@ class MyriadEngine:
         # tests/test_engine_gpu.py keeps the two paths bit-identical.
         import os
         self.use_mega = os.environ.get("MYR_MEGA", "0") == "1"
+        # MYR_GEMV=0 sends T <= 4 GEMMs back to the tcgen05 kernel (which has no fused-norm prologue)
+        self.fuse_small_batch_norm = self.FUSED_LLAMA and os.environ.get("MYR_GEMV", "1") != "0" and l_hidden_ok(dims)
 
     # ------------------------------------------------------------------------------------------ weights
     def _prep_vit(self, sd):
@@ -339,8 +346,14 @@ class MyriadEngine:
         x16, qkv, ctx, _, act = bufs
         kc, vc = self.kcache[li], self.vcache[li]
         ldq = qkv.shape[1]
-        K.norm(h32, L.n1, None, l.eps, rms=True, out16=x16)
-        K.gemm(x16, L.wqkv, out=qkv, w_static=True)
+        # T <= 4 (greedy decode at the reference's batch sizes): the small-batch weight-streaming kernel computes the RMSNorm
+        # in its own prologue, so a layer is 5 dependent launches instead of 7
+        fuse = T <= 4 and self.fuse_small_batch_norm
+        if fuse:
+            K.gemm(None, L.wqkv, out=qkv, w_static=True, norm=(h32, L.n1, l.eps))
+        else:
+            K.norm(h32, L.n1, None, l.eps, rms=True, out16=x16)
+            K.gemm(x16, L.wqkv, out=qkv, w_static=True)
         lora = (L.lora.bq, L.lora.bv, self.d.lora_r, L.lora.scale) if L.lora is not None else None  # myriad.py:171-178
         if S == 1 and dh == 128 and kv_len is not None:
             # decode: rotary + LoRA-B + cache append + attention over the cache in one CUDA-core launch
@@ -354,8 +367,11 @@ class MyriadEngine:
             K.attention(qkv, kc, vc, ctx, B, H, S, Skv, dh, 1.0 / math.sqrt(dh), (ldq, S * ldq, dh), cs, cs, (D, S * D, dh),
                         causal=causal, q_off=0, kv_len=kv_len)
         K.gemm(ctx, L.wo, res=h32, out=h32, w_static=True)
-        K.norm(h32, L.n2, None, l.eps, rms=True, out16=x16)
-        K.gemm(x16, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
+        if fuse:
+            K.gemm(None, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm=(h32, L.n2, l.eps))
+        else:
+            K.norm(h32, L.n2, None, l.eps, rms=True, out16=x16)
+            K.gemm(x16, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
         K.gemm(act, L.wd, res=h32, out=h32, w_static=True)
 
     def _llama_bufs(self, T):
@@ -395,8 +411,11 @@ class MyriadEngine:
         K.embed(self.llw.embed, st.cur_tok, st.h32)
         for li, L in enumerate(self.llw.layers):
             self._llama_layer(L, li, st.h32, st.bufs, B, 1, st.pos, st.kv_len, 0, st.cache_off, st.Skv, False)
-        K.norm(st.h32, self.llw.norm, None, l.eps, rms=True, out16=st.bufs[0])
-        K.gemm(st.bufs[0], self.llw.lm_head, out=st.logits, w_static=True)
+        if B <= 4 and self.fuse_small_batch_norm:
+            K.gemm(None, self.llw.lm_head, out=st.logits, w_static=True, norm=(st.h32, self.llw.norm, l.eps))
+        else:
+            K.norm(st.h32, self.llw.norm, None, l.eps, rms=True, out16=st.bufs[0])
+            K.gemm(st.bufs[0], self.llw.lm_head, out=st.logits, w_static=True)
         K.greedy_step(st.logits, st.state, st.scratch, B, l.vocab, st.max_new, st.min_new, l.eos, st.stops, st.n_stops,
                       st.stop_len)
 

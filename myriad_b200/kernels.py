@@ -47,6 +47,7 @@ class GemmArgs(ctypes.Structure):
         ("o_bs0", ctypes.c_int64), ("o_bs1", ctypes.c_int64),
         ("alpha_set", ctypes.c_int32), ("alpha", ctypes.c_float),
         ("pdl", ctypes.c_int32), ("w_static", ctypes.c_int32),
+        ("norm_h32", ctypes.c_void_p), ("norm_ldh", ctypes.c_int64), ("norm_gamma", ctypes.c_void_p), ("norm_eps", ctypes.c_float),
     ]
 
 
@@ -66,10 +67,17 @@ def workspace(nbytes, device):
 
 def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.float16, scale_cols=0, scale=1.0,
          round_acc=False, x_mn_major=False, w_mn_major=False, T=None, F=None, K=None, bn_hint=0, ksplit_hint=0,
-         out_group_rows=0, out_group_stride=0, ldo=None, ldx=None, ldw=None, batch=None, alpha=None, pdl=True, w_static=False):
+         out_group_rows=0, out_group_stride=0, ldo=None, ldx=None, ldw=None, batch=None, alpha=None, pdl=True, w_static=False, norm=None):
     # batch = (nb0, nb1, (x_bs0, x_bs1), (w_bs0, w_bs1), (o_bs0, o_bs1)): independent problems, element strides
-    """out[t, f] = epilogue(sum_k x[t, k] * w[f, k]);  x: [T, K] fp16 (row stride may exceed K), w: [F, K] fp16."""
-    assert x.dtype == torch.float16 and w.dtype == torch.float16
+    """out[t, f] = epilogue(sum_k x[t, k] * w[f, k]);  x: [T, K] fp16 (row stride may exceed K), w: [F, K] fp16.
+    norm = (h32 [T, K] fp32, gamma [K] fp32, eps): small-batch path only (T <= 4): x is RMSNorm(h32) * gamma computed inside
+    the kernel (pass x=None)."""
+    if norm is not None:
+        h32, gamma, eps = norm
+        assert x is None and h32.dtype == torch.float32 and gamma.dtype == torch.float32 and h32.stride(-1) == 1
+        T, K = h32.shape[0], h32.shape[1]
+        x, ldx = h32, 0  # placeholder pointer; the kernel never reads it
+    assert (norm is not None or x.dtype == torch.float16) and w.dtype == torch.float16
     assert x.stride(-1) == 1 and w.stride(-1) == 1
     assert batch is None or (T is not None and F is not None and K is not None and out is not None and ldo is not None)
     if T is None:
@@ -109,6 +117,8 @@ def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.floa
     if alpha is not None:
         a.alpha_set, a.alpha = 1, alpha
     a.pdl, a.w_static = int(pdl), int(w_static)
+    if norm is not None:
+        a.norm_h32, a.norm_ldh, a.norm_gamma, a.norm_eps = h32.data_ptr(), h32.stride(0), gamma.data_ptr(), eps
     check(lib().myr_gemm_f16(ctypes.byref(a), _stream()), "myr_gemm_f16")
     return out
 
@@ -389,6 +399,11 @@ def maxpool2(x, out, B, H, W, C):
 def greedy_step(logits, state, scratch, B, V, max_new, min_new, eos, stops, n_stops, stop_max_len):
     check(lib().myr_greedy_step(_p(logits), _i64(logits.stride(0)), B, V, _p(state), _p(scratch), max_new, min_new, eos,
                                 _p(stops), n_stops, stop_max_len, _stream()), "myr_greedy_step")
+
+
+def set_gemv(enabled):
+    """Route T <= 4 GEMMs to the small-batch CUDA-core kernel (True, default) or to the tcgen05 kernel; returns the old setting."""
+    return bool(lib().myr_set_gemv(int(bool(enabled))))
 
 
 _graph_replay_launches = 0
