@@ -250,9 +250,11 @@ def run_train_leg(args, dims, dev, world, rank, barrier):
 
 
 def roofline_probe(eng, dims, dev, peaks):
-    """Dominant kernel = gemm_tc_kernel in its decode (weight-streaming) configuration: ~85 % of a step is the 32 decode
-    steps, each streaming every LLaMA weight once. Timed live with CUDA events over the real 32 layers' weights in layer
-    order (13 GB >> L2, so nothing is re-served from cache). Also reports the tensor-bound ViT GEMM for context."""
+    """Dominant kernel = the small-batch weight-streaming kernel (csrc/gemv.cu, `gemv_kernel`): ~75 % of a step is the 32
+    decode steps, each streaming every LLaMA weight once through 4 launches per layer. Timed live with CUDA events over the
+    real 32 layers' weights in layer order and in the decode step's own launch configuration (fused RMSNorm prologues,
+    in-place fp32 residual, SwiGLU epilogue; 13 GB >> L2, so nothing is re-served from cache). Also reports the tensor-bound
+    ViT GEMM for context."""
     import torch
 
     from myriad_b200 import kernels as K
@@ -264,12 +266,19 @@ def roofline_probe(eng, dims, dev, peaks):
     qkv = torch.empty(B, wq, device=dev, dtype=torch.float16)
     o = torch.zeros(B, l.hidden, device=dev, dtype=torch.float32)
     act = torch.empty(B, l.inter, device=dev, dtype=torch.float16)
+    fused = eng.fuse_small_batch_norm and B <= 4
 
     def sweep():
         for L in eng.llw.layers:
-            K.gemm(x, L.wqkv, out=qkv, w_static=True)
+            if fused:
+                K.gemm(None, L.wqkv, out=qkv, w_static=True, norm=(o, L.n1, l.eps))
+            else:
+                K.gemm(x, L.wqkv, out=qkv, w_static=True)
             K.gemm(x, L.wo, res=o, out=o, w_static=True)
-            K.gemm(x, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
+            if fused:
+                K.gemm(None, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm=(o, L.n2, l.eps))
+            else:
+                K.gemm(x, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
             K.gemm(a, L.wd, res=o, out=o, w_static=True)
 
     for _ in range(2):
@@ -277,6 +286,7 @@ def roofline_probe(eng, dims, dev, peaks):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
+    o.zero_()
     e0.record()
     for _ in range(reps):
         sweep()
@@ -285,13 +295,16 @@ def roofline_probe(eng, dims, dev, peaks):
     ms = e0.elapsed_time(e1) / reps
     n_launch = 4 * l.layers
     wbytes = l.layers * 2 * (wq * l.hidden + l.hidden * l.hidden + 2 * l.inter * l.hidden + l.hidden * l.inter)
-    # activations per layer: x read 3x (fp16), act read once, qkv / act written (fp16), fp32 residual read + written twice
-    abytes = l.layers * B * (3 * 2 * l.hidden + 2 * l.inter + 2 * wq + 2 * l.inter + 2 * 8 * l.hidden)
+    # activations per layer: the two normed projections read the fp32 residual rows + gamma, o / down read fp16 rows and read +
+    # write the fp32 residual; qkv / act are written in fp16
+    abytes = l.layers * (2 * (B * 4 * l.hidden + 4 * l.hidden) + B * 2 * l.hidden + B * 2 * l.inter + 2 * 2 * B * 4 * l.hidden +
+                         B * 2 * wq + B * 2 * l.inter)
     per_launch = (wbytes + abytes) / n_launch
     achieved = (wbytes + abytes) / (ms / 1e3) / 1e9
-    roof = {"kernel": "gemm_tc_kernel (decode, T=%d: qkv+loraA / o+res / gate_up+swiglu / down+res of all 32 layers)" % B, "bound": "hbm", "achieved": achieved,
-            "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-            "avg_launch_us": ms * 1e3 / n_launch, "algorithmic_bytes_per_launch": per_launch}
+    kname = "gemv_kernel" if fused else "gemm_tc_kernel"
+    roof = {"kernel": "%s (decode, T=%d: norm+qkv+loraA / o+res / norm+gate_up+swiglu / down+res of all 32 layers)" % (kname, B), "bound": "hbm",
+            "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
+            "peak_source": peaks["src"], "avg_launch_us": ms * 1e3 / n_launch, "algorithmic_bytes_per_launch": per_launch}
     # tensor-bound context: the ViT MLP GEMMs at the bench batch (T = B * 257)
     T, D, Hd = B * dims.vit.tokens, dims.vit.dim, dims.vit.mlp_hidden
     h = torch.randn(T, D, device=dev).half()

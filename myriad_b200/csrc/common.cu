@@ -53,6 +53,14 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static void* g_trace = nullptr;
+void set_trace_buffer(void* buf) { g_trace = buf; }
+long long* next_trace_slot() {
+  long long* t = reinterpret_cast<long long*>(g_trace);
+  if (g_trace) g_trace = reinterpret_cast<char*>(g_trace) + 148 * 6 * sizeof(long long);
+  return t;
+}
+
 int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();

@@ -12,6 +12,9 @@
 namespace myr {
 
 void set_error(const char* fmt, ...);
+// Profiling aid (myr_gemm_set_trace): next 148 x 6 int64 slot of the trace buffer, or null when tracing is off.
+long long* next_trace_slot();
+void set_trace_buffer(void* buf);
 void count_launch();
 int sm_count();
 

@@ -11,12 +11,192 @@
 
 namespace myr {
 
+// Stand-alone kernel: same arithmetic and reduction order as decode_attn_task (decode_attn.cuh, used by the persistent
+// decode kernel), restructured around the dependency on the previous kernel. Only the NEW token's q / k / v come from the
+// qkv projection running right before this kernel; every cached key / value row was written one or more decode steps (or a
+// host-synchronised prefill) ago. So the first 128 K rows (one key per thread) are requested BEFORE the programmatic-
+// dependent-launch wait and are in registers by the time q exists (the rest of K and all of V are pulled into L2 at the
+// same time), and the first 128 V rows are requested as soon as the K registers are free, so their latency hides behind the softmax barriers: the kernel's critical path after the projection is
+// LoRA + RoPE -> dot products -> softmax -> P V on register-resident data, instead of three dependent trips to the cache.
+// Dependents are released first: the o_proj kernel behind this one fills its weight ring while attention runs.
 __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAttnParams p) {
   extern __shared__ float s_scores[];  // [Smax]
   __shared__ DecodeAttnSmem sm;
-  pdl_wait();
   pdl_launch_dependents();
-  decode_attn_task(p, blockIdx.x, blockIdx.y, threadIdx.x, sm, s_scores, [] { __syncthreads(); });
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  long long* tr = (p.trace && tid == 0) ? p.trace + (blockIdx.y * gridDim.x + blockIdx.x) * 6 : nullptr;
+  auto stamp = [&](int i) {
+    if (tr) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      tr[i] = t;
+    }
+  };
+  stamp(0);
+  const int warp = tid >> 5, lane = tid & 31;
+  const int HD = p.H * DA_DH;
+  // step state (cache slot, visible length) is written by the greedy-update kernel at the END of the previous decode step,
+  // i.e. before the kernels in front of this one could start: safe to read ahead of the wait
+  const int off = p.cache_off ? __ldcg(p.cache_off) : p.cache_off_host;
+  int kvl = p.kv_len ? __ldcg(p.kv_len + b) : off + 1;
+  if (kvl > p.Smax) kvl = p.Smax;
+  __half* kbase = p.kcache + (size_t)b * p.c_bs + h * DA_DH;
+  __half* vbase = p.vcache + (size_t)b * p.c_bs + h * DA_DH;
+
+  uint4 kA[DA_DH / 8];
+  uint2 vA[16], vB[16];
+  auto load_k = [&](uint4 (&kv)[DA_DH / 8], int j) {
+    if (j < kvl && j != off) {
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + (size_t)j * p.c_ts);
+#pragma unroll
+      for (int i = 0; i < DA_DH / 8; ++i) kv[i] = kp[i];
+    }
+  };
+  auto load_v = [&](uint2 (&vv)[16], int j0) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = j0 + 4 * u;
+      if (j < kvl && j != off) vv[u] = *reinterpret_cast<const uint2*>(vbase + (size_t)j * p.c_ts + lane * 4);
+    }
+  };
+  load_k(kA, tid);
+  if (tid + DA_THREADS < kvl && tid + DA_THREADS != off) {  // second key of this thread: into L2 now, into registers after phase 0
+    prefetch_l2(kbase + (size_t)(tid + DA_THREADS) * p.c_ts);
+    prefetch_l2(kbase + (size_t)(tid + DA_THREADS) * p.c_ts + 64);
+  }
+  for (int j = tid; j < 2 * kvl; j += DA_THREADS) prefetch_l2(vbase + (size_t)(j >> 1) * p.c_ts + (j & 1) * 64);
+  const int pos = __ldcg(p.pos + b);
+  const int jr = tid & (DA_DH / 2 - 1);
+  const float c = p.cos_t[(size_t)pos * (DA_DH / 2) + jr], sn = p.sin_t[(size_t)pos * (DA_DH / 2) + jr];
+  pdl_wait();
+  stamp(1);
+
+  // ---- phase 0: q / k / v of the new token: LoRA, rotation, cache append (one rotary pair per thread)
+  const __half* row = p.qkv + (size_t)b * p.ldq;
+  if (tid < DA_DH / 2) {
+    const int j = tid, half = DA_DH / 2;
+    float q1 = __half2float(__ldcg(row + h * DA_DH + j)), q2 = __half2float(__ldcg(row + h * DA_DH + half + j));
+    const float k1 = __half2float(__ldcg(row + HD + h * DA_DH + j)), k2 = __half2float(__ldcg(row + HD + h * DA_DH + half + j));
+    float v1 = __half2float(__ldcg(row + 2 * HD + h * DA_DH + j)), v2 = __half2float(__ldcg(row + 2 * HD + h * DA_DH + half + j));
+    if (p.lora_r) {
+      float xq[8], xv[8];
+      da_unpack8(__ldcg(reinterpret_cast<const uint4*>(row + 3 * HD)), xq);
+      da_unpack8(__ldcg(reinterpret_cast<const uint4*>(row + 3 * HD + 8)), xv);
+      q1 = fmaf(p.lora_scale, da_lora_dot(p.lora_bq, h * DA_DH + j, xq), q1);
+      q2 = fmaf(p.lora_scale, da_lora_dot(p.lora_bq, h * DA_DH + half + j, xq), q2);
+      v1 = fmaf(p.lora_scale, da_lora_dot(p.lora_bv, h * DA_DH + j, xv), v1);
+      v2 = fmaf(p.lora_scale, da_lora_dot(p.lora_bv, h * DA_DH + half + j, xv), v2);
+    }
+    // fp16 rounding of the rotated q / k and of v: the values the prefill path stores (q in place, k / v in the cache)
+    sm.q[j] = round_f16(q1 * c - q2 * sn);
+    sm.q[half + j] = round_f16(q2 * c + q1 * sn);
+    const __half ko1 = __float2half_rn(k1 * c - k2 * sn), ko2 = __float2half_rn(k2 * c + k1 * sn);
+    const __half vo1 = __float2half_rn(v1), vo2 = __float2half_rn(v2);
+    sm.k[j] = ko1; sm.k[half + j] = ko2;
+    sm.v[j] = vo1; sm.v[half + j] = vo2;
+    if (off >= 0 && off < p.Smax) {
+      __half* kd = kbase + (size_t)off * p.c_ts;
+      __half* vd = vbase + (size_t)off * p.c_ts;
+      kd[j] = ko1; kd[half + j] = ko2;
+      vd[j] = vo1; vd[half + j] = vo2;
+    }
+  }
+  __syncthreads();
+  stamp(2);
+
+  // ---- phase 1: scores, one key per thread and batch of 128 keys; the next batch is in flight while this one is reduced
+  auto score = [&](const uint4 (&kv)[DA_DH / 8], int j) {
+    if (j < kvl) {
+      const uint4* ks = reinterpret_cast<const uint4*>(sm.k);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < DA_DH / 8; ++i) {
+        float kf[8];
+        da_unpack8(j == off ? ks[i] : kv[i], kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d = fmaf(kf[e], sm.q[i * 8 + e], d);
+      }
+      s_scores[j] = d * p.scale;
+    }
+  };
+#pragma unroll 1
+  for (int j = tid; j < kvl; j += DA_THREADS) {
+    if (j != tid) load_k(kA, j);  // keys beyond the first 128: L2 hits (prefetched above)
+    score(kA, j);
+  }
+  __syncthreads();
+  stamp(3);
+  // the K registers are dead: request the first two V batches now, their latency hides behind the softmax barriers
+  load_v(vA, warp);
+  load_v(vB, warp + 64);
+
+  // ---- softmax statistics (fp32)
+  float m = -INFINITY;
+  for (int j = tid; j < kvl; j += DA_THREADS) m = fmaxf(m, s_scores[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) sm.red[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(sm.red[0], sm.red[1]), fmaxf(sm.red[2], sm.red[3]));
+  __syncthreads();
+  float l = 0.f;
+  for (int j = tid; j < kvl; j += DA_THREADS) {
+    const float e = __expf(s_scores[j] - m);
+    s_scores[j] = e;
+    l += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if (lane == 0) sm.red[warp] = l;
+  __syncthreads();
+  l = (sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]);
+  stamp(4);
+
+  // ---- phase 2: O = P V. Warp w owns keys j = w (mod 4); lane l owns dims [4l, 4l + 4); batches of 16 keys per warp
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  auto pv = [&](const uint2 (&vv)[16], int j0) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = j0 + 4 * u;
+      if (j < kvl) {
+        const float pj = s_scores[j];
+        const uint2 raw = (j == off) ? *reinterpret_cast<const uint2*>(sm.v + lane * 4) : vv[u];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+        const float2 a = __half22float2(h2[0]), bb = __half22float2(h2[1]);
+        acc[0] = fmaf(pj, a.x, acc[0]);
+        acc[1] = fmaf(pj, a.y, acc[1]);
+        acc[2] = fmaf(pj, bb.x, acc[2]);
+        acc[3] = fmaf(pj, bb.y, acc[3]);
+      }
+    }
+  };
+#pragma unroll 1
+  for (int j0 = warp; j0 < kvl; j0 += 128) {
+    pv(vA, j0);
+    load_v(vA, j0 + 128);  // L2 hits (prefetched before the wait)
+    pv(vB, j0 + 64);
+    load_v(vB, j0 + 192);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sm.acc[warp][lane * 4 + i] = acc[i];
+  if (p.next_layer_stride) {
+    // The next layer's attention reads the same (head, row) slice of ITS cache ~100 us from now. At decode the cache is
+    // touched once per step, so those lines sit in DRAM and, under the weight stream, a miss costs microseconds of a
+    // latency-bound kernel: ask L2 for them now (weights are loaded evict-first, so the lines survive until then).
+    const __half* kn = kbase + p.next_layer_stride;
+    const __half* vn = vbase + p.next_layer_stride;
+    for (int j = tid; j < 2 * kvl; j += DA_THREADS) {  // one 128-byte line = half a K or V row
+      const size_t o = (size_t)(j >> 1) * p.c_ts + (j & 1) * 64;
+      prefetch_l2(kn + o);
+      prefetch_l2(vn + o);
+    }
+  }
+  __syncthreads();
+  {
+    const float o = (sm.acc[0][tid] + sm.acc[1][tid]) + (sm.acc[2][tid] + sm.acc[3][tid]);
+    p.out[(size_t)b * p.ldo + h * DA_DH + tid] = __float2half_rn(l > 0.f ? o / l : 0.f);
+  }
+  stamp(5);
 }
 
 }  // namespace myr
@@ -47,6 +227,14 @@ extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_
   p.scale = a->scale;
   p.out = reinterpret_cast<__half*>(a->out); p.ldo = a->ldo;
   p.next_layer_stride = a->next_layer_stride;
+  p.trace = (a->B * a->H <= 148) ? next_trace_slot() : nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    // same L1 / shared-memory split as the weight-streaming kernels around it: an SM only hosts CTAs of two kernels at once
+    // when their carve-outs agree, and this kernel wants to sit next to the qkv projection (K pre-load) and under o_proj
+    MYR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set = true;
+  }
   MYR_CHECK_CUDA(launch_kernel(decode_attn_kernel, dim3(a->H, a->B), dim3(DA_THREADS), (size_t)a->cache_len * sizeof(float), stream,
                                true, p));
   MYR_CHECK_LAUNCH();

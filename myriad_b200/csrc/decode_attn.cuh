@@ -21,6 +21,7 @@ struct DecodeAttnParams {
   float scale;
   __half* out; long long ldo;        // [B, H * dh]
   long long next_layer_stride;       // elements from this layer's cache to the next layer's (0: none): L2 prefetch hint
+  long long* trace;                  // debug: 6 x %globaltimer ns per CTA (myr_gemm_set_trace); stand-alone kernel only
 };
 
 __device__ __forceinline__ void da_unpack8(const uint4& u, float (&f)[8]) {

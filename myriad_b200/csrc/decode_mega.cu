@@ -690,6 +690,7 @@ extern "C" int myr_mega_plan(const myr_mega_op* ops, int32_t n_ops, void* host_b
       q.scale = a->scale;
       q.out = reinterpret_cast<__half*>(a->out); q.ldo = a->ldo;
       q.next_layer_stride = 0;  // the persistent kernel prefetches the slice itself while the qkv weights stream
+      q.trace = nullptr;
       d.n_tasks = a->B * a->H;
     } else if (s.kind == MG_GEMM) {
       MYR_CHECK_ARG(s.x && s.w && s.out && s.T > 0 && s.T <= MG_TMAX && s.F > 0 && s.K > 0, "mega_plan: op %d: bad GEMM (T <= %d)", i, MG_TMAX);

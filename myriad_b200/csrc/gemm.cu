@@ -758,9 +758,8 @@ static Plan make_plan(const myr_gemm_args* a, int nbatch, bool allow_split, size
 
 using namespace myr;
 
-static void* g_gemm_trace = nullptr;
 /* debug: every following GEMM launch writes 148 x 6 timestamps at `buf` and advances it (NULL stops tracing) */
-extern "C" void myr_gemm_set_trace(void* buf) { g_gemm_trace = buf; }
+extern "C" void myr_gemm_set_trace(void* buf) { set_trace_buffer(buf); }
 
 extern "C" size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K) {
   (void)K;
@@ -787,7 +786,7 @@ extern "C" int32_t myr_set_gemv(int32_t enabled) {
 
 static bool gemv_eligible(const myr_gemm_args* a, int nbatch) {
   return a->T <= 4 && !a->x_mn_major && !a->w_mn_major && nbatch == 1 && a->scale_cols == 0 && !a->round_acc && !a->alpha_set &&
-         a->out_group_rows == 0 && (a->act == MYR_ACT_NONE || a->act == MYR_ACT_SWIGLU) && a->K % 128 == 0 && a->bn_hint == 0 &&
+         a->out_group_rows == 0 && (a->act == MYR_ACT_NONE || a->act == MYR_ACT_SWIGLU) && a->K % 128 == 0 && a->K <= 32768 && a->bn_hint == 0 &&
          a->ksplit_hint == 0;
 }
 
@@ -883,8 +882,7 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   p.partial = partial; p.counters = counters;
   p.nb1 = nb1; p.nbatch = nbatch; p.o_bs0 = a->o_bs0; p.o_bs1 = a->o_bs1;
   p.n_mp = pl.n_mp;
-  p.trace = reinterpret_cast<long long*>(g_gemm_trace);
-  if (g_gemm_trace) g_gemm_trace = reinterpret_cast<char*>(g_gemm_trace) + 148 * 6 * sizeof(long long);  // next launch, next slot
+  p.trace = next_trace_slot();  // next launch, next slot
   // weights may be prefetched ahead of the dependency only when they are the K-major A operand and the caller says so
   p.w_static = (a->w_static && !pl.row_mode && !a_mn) ? 1 : 0;
   if (pl.row_mode) {

@@ -28,7 +28,12 @@ namespace myr {
 
 constexpr int GV_CWARPS = 8;                      // consumer (MMA) warps
 constexpr int GV_CTHREADS = GV_CWARPS * 32;
-constexpr int GV_THREADS = GV_CTHREADS + 32;      // + one producer warp (TMA issue)
+constexpr int GV_SWARPS = 2;                      // activation-staging warps
+constexpr int GV_STHREADS = GV_SWARPS * 32;
+constexpr int GV_THREADS = GV_CTHREADS + 32 + GV_STHREADS;  // consumers + one producer warp (TMA issue) + stagers
+constexpr int GV_MAX_KC = 32;                     // k stages per row: K <= 32768
+constexpr int GV_HK = 512;                        // k per TMA transfer of the fp32 residual rows (fused RMSNorm)
+constexpr int GV_HBUF_BYTES = (4 + 1) * GV_HK * 4;  // GV_T rows + the gamma slice: 10 KiB
 constexpr int GV_UR = 8;                          // weight rows per unit = rows of one TMA box
 constexpr int GV_T = 4;                           // activation rows held in shared memory (the N side holds 8; rows >= T are zero)
 constexpr int GV_WK = 128;                        // k elements per consumer warp and stage
@@ -38,7 +43,6 @@ constexpr int GV_BOX_BYTES = GV_UR * GV_BOX_K * 2;  // 8 KiB
 constexpr int GV_STAGE_BYTES = 4 * GV_BOX_BYTES;  // 16 rows x 1024 k: boxes [k half][row half]
 constexpr int GV_MAX_STAGES = 6;
 constexpr int GV_SMEM_BUDGET = 227 * 1024;        // max dynamic shared memory per CTA on sm_100
-constexpr int GV_NORM_VEC = 4;                    // float4 per (row, thread) held by the fused RMSNorm: K <= 4096
 constexpr int GV_XPAD = 8;                        // halfs of padding per activation row (bank spread)
 
 struct GemvParams {
@@ -55,8 +59,19 @@ struct GemvParams {
   int max_groups;                                 // row groups of the largest CTA slice (sizes the partial-sum buffer)
   int stages;
   int w_static;
+  long long* trace;                               // debug: 6 x %globaltimer ns per CTA (myr_gemm_set_trace)
 };
+__device__ __forceinline__ long long gv_time() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -78,7 +93,7 @@ __device__ __forceinline__ int gv_half_row0(const GemvParams& p, int ub, int n_u
   return ((i0 >> 6) << 7) + (i0 & 63) + (half << 6);
 }
 
-__global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const __grid_constant__ CUtensorMap tmW, const GemvParams p) {
+__global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap tmW, const GemvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -92,20 +107,29 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const __grid_consta
   uint8_t* ring = smem;
   __half* xs = reinterpret_cast<__half*>(ring + (size_t)p.stages * GV_STAGE_BYTES);       // [GV_T][xld]
   float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)GV_T * xld * 2);  // [warps][GV_T]
-  float4* red = reinterpret_cast<float4*>(s_part + GV_CWARPS * GV_T);                       // [warps][max_groups][32 lanes]
-  uint64_t* full = reinterpret_cast<uint64_t*>(red + (size_t)GV_CWARPS * p.max_groups * 32);  // [stages] producer -> consumers
+  float4* red = reinterpret_cast<float4*>(s_part + GV_CWARPS * GV_T);                       // [warps][max_groups][16 lanes]
+  float* hbuf = reinterpret_cast<float*>(red + (size_t)GV_CWARPS * p.max_groups * 16);      // [GV_T][GV_HK] fp32 (fused RMSNorm only)
+  uint64_t* full = reinterpret_cast<uint64_t*>(hbuf + (p.h32 ? (GV_T + 1) * GV_HK : 0));          // [stages] producer -> consumers
   uint64_t* empty = full + GV_MAX_STAGES;                                                     // [stages] consumers -> producer
+  uint64_t* xbar = empty + GV_MAX_STAGES;                                                     // [n_kc] activation chunk kc staged
+  uint64_t* rbar = xbar + GV_MAX_KC;                                                          // RMSNorm scale ready
+  uint64_t* hbar = rbar + 1;                                                                  // staging buffer filled
+  float* s_rstd = reinterpret_cast<float*>(hbar + 1);                                         // [GV_T]
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], GV_CWARPS);
     }
+    for (int kc = 0; kc < p.n_kc; ++kc) mbar_init(&xbar[kc], p.h32 ? GV_STHREADS : 1);
+    mbar_init(rbar, 1);
+    mbar_init(hbar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmW);
   }
   __syncthreads();
   pdl_launch_dependents();
+  if (p.trace && tid == 0) p.trace[blockIdx.x * 6 + 0] = gv_time();  // CTA start
 
   if (warp == GV_CWARPS) {
     // ------------------------------ producer: one thread, up to 4 boxes of 8 KiB per stage ------------------------------
@@ -130,10 +154,102 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const __grid_consta
           st = 0;
           phase ^= 1;
         }
-        if (++kc == p.n_kc) {
-          kc = 0;
-          ++g;
+        if (++g == n_groups) {
+          g = 0;
+          ++kc;
         }
+      }
+    }
+    return;
+  }
+
+  if (warp > GV_CWARPS) {
+    // ------------------------------ stagers: activations -> shared fp16 [GV_T][xld], one 1024-k chunk at a time ------------------------------
+    // The consumers walk K in the same order (chunk outer, row groups inner), so they start on chunk 0 while the rest is
+    // still being staged: the ~2 TB/s at which L2 serves the same activation lines to all 148 CTAs stays off the critical path.
+    const int stid = tid - GV_CTHREADS - 32;
+    if (p.h32 == nullptr) {
+      // rows >= T are never copied: zero them once
+      for (int i = stid; i < (GV_T - p.T) * (xld >> 3); i += GV_STHREADS)
+        *reinterpret_cast<uint4*>(xs + (size_t)p.T * xld + i * 8) = make_uint4(0u, 0u, 0u, 0u);
+      asm volatile("bar.sync 2, %0;" ::"n"(GV_STHREADS) : "memory");
+      if (stid == 0) {
+        fence_proxy_async_smem();
+        pdl_wait();
+        for (int kc = 0; kc < p.n_kc; ++kc) {
+          const int k0 = kc * GV_SK;
+          const uint32_t bytes = (uint32_t)min(GV_SK, p.K - k0) * 2;
+          mbar_arrive_expect_tx(&xbar[kc], bytes * p.T);
+          for (int t = 0; t < p.T; ++t)
+            bulk_g2s(smem_u32(xs + (size_t)t * xld + k0), p.x + (long long)t * p.ldx + k0, bytes, smem_u32(&xbar[kc]));
+        }
+      }
+    } else {
+      // LlamaRMSNorm (modeling_llama.py:66-74): x = h * rsqrt(mean(h^2) + eps) * gamma. The per-token scale is a scalar, so
+      // it is applied in the epilogue (the GEMV is linear in x) and the chunks of rn_f16(h * gamma) can be staged while the
+      // sum of squares is still being accumulated.
+      // The fp32 rows arrive by TMA bulk copy, 512 k at a time, in an 8 KiB staging buffer (LSU loads issued under the
+      // saturated weight stream take ~2.5 us per round trip on B200; the TMA path does not queue behind it).
+      float ss[GV_T] = {0.f, 0.f, 0.f, 0.f};
+      const float4* hb4 = reinterpret_cast<const float4*>(hbuf);
+      const float4* gb4 = hb4 + GV_T * (GV_HK / 4);   // gamma slice rides along in the same transfer group
+      const int n_half = (p.K + GV_HK - 1) / GV_HK;
+      pdl_wait();
+      if (p.trace && stid == 0) p.trace[blockIdx.x * 6 + 1] = gv_time();  // predecessor released
+      uint32_t hph = 0;
+      for (int hh = 0; hh < n_half; ++hh) {
+        const int k0 = hh * GV_HK;
+        const int nk = min(GV_HK, p.K - k0);
+        if (stid == 0) {
+          mbar_arrive_expect_tx(hbar, (uint32_t)((p.T + 1) * nk * 4));
+          for (int t = 0; t < p.T; ++t) bulk_g2s(smem_u32(hbuf + t * GV_HK), p.h32 + (long long)t * p.ldh + k0, (uint32_t)nk * 4, smem_u32(hbar));
+          bulk_g2s(smem_u32(hbuf + GV_T * GV_HK), p.gamma + k0, (uint32_t)nk * 4, smem_u32(hbar));
+        }
+        mbar_wait(hbar, hph);
+        hph ^= 1;
+#pragma unroll
+        for (int t = 0; t < GV_T; ++t) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = stid + j * GV_STHREADS;
+            if (c * 4 < nk) {
+              const float4 v = t < p.T ? hb4[t * (GV_HK / 4) + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+              ss[t] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+              const float4 gm = gb4[c];
+              const __half2 a = __floats2half2_rn(v.x * gm.x, v.y * gm.y);
+              const __half2 b = __floats2half2_rn(v.z * gm.z, v.w * gm.w);
+              uint2 u;
+              u.x = *reinterpret_cast<const uint32_t*>(&a);
+              u.y = *reinterpret_cast<const uint32_t*>(&b);
+              *reinterpret_cast<uint2*>(xs + (size_t)t * xld + k0 + c * 4) = u;
+            }
+          }
+        }
+        if ((hh & 1) || hh == n_half - 1) {
+          mbar_arrive(&xbar[hh >> 1]);  // both halves of the 1024-k chunk are staged (this thread's part)
+          if (p.trace && stid == 0 && hh <= 1) p.trace[blockIdx.x * 6 + 3] = gv_time();  // fused RMSNorm: first 1024-k chunk staged
+          if (p.trace && stid == 0 && hh == n_half - 1) p.trace[blockIdx.x * 6 + 4] = gv_time();  // fused RMSNorm: all chunks staged
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(GV_STHREADS) : "memory");  // staging buffer free for the next copy
+      }
+#pragma unroll
+      for (int t = 0; t < GV_T; ++t) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss[t] += __shfl_xor_sync(0xffffffffu, ss[t], o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < GV_T; ++t) s_part[(warp - GV_CWARPS - 1) * GV_T + t] = ss[t];
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(GV_STHREADS) : "memory");
+      if (stid == 0) {
+#pragma unroll
+        for (int t = 0; t < GV_T; ++t) {
+          float tot = 0.f;
+          for (int w = 0; w < GV_SWARPS; ++w) tot += s_part[w * GV_T + t];
+          s_rstd[t] = rsqrtf(tot / p.K + p.eps);
+        }
+        mbar_arrive(rbar);
       }
     }
     return;
@@ -141,62 +257,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const __grid_consta
 
   // ------------------------------ consumers ------------------------------
   pdl_wait();
-  // ---- activations -> shared fp16 [GV_T][xld] (zero padded) ----
-  if (p.h32 == nullptr) {
-    const int kv8 = p.kp >> 3;
-    for (int i = tid; i < GV_T * kv8; i += GV_CTHREADS) {
-      const int t = i / kv8, k8 = i - t * kv8;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (t < p.T && k8 * 8 < p.K) v = *reinterpret_cast<const uint4*>(p.x + (long long)t * p.ldx + k8 * 8);
-      *reinterpret_cast<uint4*>(xs + (size_t)t * xld + k8 * 8) = v;
-    }
-  } else {
-    // LlamaRMSNorm (modeling_llama.py:66-74) with fp32 statistics; same rounding point as norm_kernel (one fp16 rounding
-    // of x * rstd * gamma)
-    const int nvec = p.K >> 2;
-    float4 v[GV_T][GV_NORM_VEC];
-    float ss[GV_T];
-#pragma unroll
-    for (int t = 0; t < GV_T; ++t) {
-      ss[t] = 0.f;
-#pragma unroll
-      for (int j = 0; j < GV_NORM_VEC; ++j) {
-        const int c = tid + j * GV_CTHREADS;
-        v[t][j] = (t < p.T && c < nvec) ? reinterpret_cast<const float4*>(p.h32 + (long long)t * p.ldh)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-        ss[t] += v[t][j].x * v[t][j].x + v[t][j].y * v[t][j].y + v[t][j].z * v[t][j].z + v[t][j].w * v[t][j].w;
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < GV_T; ++t) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ss[t] += __shfl_xor_sync(0xffffffffu, ss[t], o);
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int t = 0; t < GV_T; ++t) s_part[warp * GV_T + t] = ss[t];
-    }
-    consumer_sync();
-#pragma unroll
-    for (int t = 0; t < GV_T; ++t) {
-      float tot = 0.f;
-      for (int w = 0; w < GV_CWARPS; ++w) tot += s_part[w * GV_T + t];
-      const float rstd = rsqrtf(tot / p.K + p.eps);
-#pragma unroll
-      for (int j = 0; j < GV_NORM_VEC; ++j) {
-        const int c = tid + j * GV_CTHREADS;
-        if (c < nvec) {
-          const float4 g = reinterpret_cast<const float4*>(p.gamma)[c];
-          const __half2 a = __floats2half2_rn(v[t][j].x * rstd * g.x, v[t][j].y * rstd * g.y);
-          const __half2 b = __floats2half2_rn(v[t][j].z * rstd * g.z, v[t][j].w * rstd * g.w);
-          uint2 u;
-          u.x = *reinterpret_cast<const uint32_t*>(&a);
-          u.y = *reinterpret_cast<const uint32_t*>(&b);
-          *reinterpret_cast<uint2*>(xs + (size_t)t * xld + c * 4) = u;
-        }
-      }
-    }
-  }
-  consumer_sync();
+  if (p.trace && tid == 0 && !p.h32) p.trace[blockIdx.x * 6 + 1] = gv_time();  // predecessor released
 
   // ---- main loop: per iteration this warp multiplies its 16 x 128 slice of the stage with its 128 x 8 slice of x ----
   // Stage layout = 4 TMA boxes [k half][row half], each [8 k-blocks][8 rows][128 bytes] with the 128-byte swizzle (16-byte
@@ -206,23 +267,32 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const __grid_consta
   const int a_r = lane & 7, a_rh = (lane >> 3) & 1, a_hi = lane >> 4;
   // this warp's 128 k = k-blocks 2 * (warp % 4), + 1 of k half warp / 4
   const uint32_t a_lane = smem_u32(ring) + ((warp >> 2) * 2 + a_rh) * GV_BOX_BYTES + (warp & 3) * 2 * 1024 + a_r * 128;
-  float4* red_w = red + (size_t)warp * p.max_groups * 32 + lane;
+  // D fragment: lane l holds tokens 2 * (l % 4) + {0, 1}: only lanes with l % 4 < 2 carry tokens 0..3
+  const bool d_lane = (lane & 3) < 2;
+  float4* red_w = red + (size_t)warp * p.max_groups * 16 + (lane >> 2) * 2 + (lane & 1);
   const int b_n = lane >> 2, b_k = (lane & 3) * 2;
   const __half* xb = xs + (size_t)(b_n < GV_T ? b_n : 0) * xld + warp * GV_WK + b_k;
   int g = 0, kc = 0, st = 0;
   uint32_t phase = 0;
-  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t bfrag[GV_WK / 16][2];
+  bool mine = false;
   for (int it = 0; it < n_it; ++it) {
-    const bool mine = kc * GV_SK + warp * GV_WK < p.K;  // K is a multiple of 128: a warp's slice is whole or absent
-    uint32_t bfrag[GV_WK / 16][2];
-    if (mine) {
+    if (g == 0) {
+      // next 1024-k chunk of the activations: wait until it is staged, then keep this warp's 128 x 8 slice in registers
+      mine = kc * GV_SK + warp * GV_WK < p.K;  // K is a multiple of 128: a warp's slice is whole or absent
+      mbar_wait(&xbar[kc], 0);
+      if (p.trace && tid == 0 && it == 0) p.trace[blockIdx.x * 6 + 2] = gv_time();  // first activation chunk staged
+      if (mine) {
 #pragma unroll
-      for (int ks = 0; ks < GV_WK / 16; ++ks) {
-        bfrag[ks][0] = b_n < GV_T ? *reinterpret_cast<const uint32_t*>(xb + kc * GV_SK + ks * 16) : 0u;
-        bfrag[ks][1] = b_n < GV_T ? *reinterpret_cast<const uint32_t*>(xb + kc * GV_SK + ks * 16 + 8) : 0u;
+        for (int ks = 0; ks < GV_WK / 16; ++ks) {
+          bfrag[ks][0] = b_n < GV_T ? *reinterpret_cast<const uint32_t*>(xb + kc * GV_SK + ks * 16) : 0u;
+          bfrag[ks][1] = b_n < GV_T ? *reinterpret_cast<const uint32_t*>(xb + kc * GV_SK + ks * 16 + 8) : 0u;
+        }
       }
     }
     mbar_wait(&full[st], phase);
+    if (p.trace && tid == 0 && it == 0 && !p.h32) p.trace[blockIdx.x * 6 + 3] = gv_time();  // first stage landed
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
     if (mine) {
       const uint32_t a_st = a_lane + (uint32_t)st * GV_STAGE_BYTES;
 #pragma unroll
@@ -234,28 +304,37 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const __grid_consta
     }
     __syncwarp();  // every lane's ldmatrix of this stage is done before the stage is handed back
     if (lane == 0) mbar_arrive(&empty[st]);
+    // running sum over the k chunks of this (warp, row group), in chunk order
+    if (d_lane) {
+      float4 acc = make_float4(d[0], d[1], d[2], d[3]);
+      if (kc > 0) {
+        const float4 o = red_w[g * 16];
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      red_w[g * 16] = acc;
+    }
     if (++st == p.stages) {
       st = 0;
       phase ^= 1;
     }
-    if (++kc == p.n_kc) {
-      red_w[g * 32] = make_float4(d[0], d[1], d[2], d[3]);
-      d[0] = d[1] = d[2] = d[3] = 0.f;
-      kc = 0;
-      ++g;
+    if (++g == n_groups) {
+      g = 0;
+      ++kc;
     }
   }
+  if (p.h32) mbar_wait(rbar, 0);
   consumer_sync();
+  if (p.trace && tid == 0 && !p.h32) p.trace[blockIdx.x * 6 + 4] = gv_time();  // last stage consumed
 
   // ---- cross-warp sum in warp order + epilogue ----
   // D fragment: lane l holds (row l/4, token 2*(l%4) + {0,1}) in .x/.y and (row l/4 + 8, same tokens) in .z/.w
   const float* redf = reinterpret_cast<const float*>(red);
   auto total = [&](int gg, int rr, int t) {
-    const int l = (rr & 7) * 4 + (t >> 1), j = (t & 1) + 2 * (rr >> 3);
+    const int l = (rr & 7) * 2 + (t >> 1), j = (t & 1) + 2 * (rr >> 3);
     float a = 0.f;
 #pragma unroll
-    for (int w = 0; w < GV_CWARPS; ++w) a += redf[(((size_t)w * p.max_groups + gg) * 32 + l) * 4 + j];
-    return a;
+    for (int w = 0; w < GV_CWARPS; ++w) a += redf[(((size_t)w * p.max_groups + gg) * 16 + l) * 4 + j];
+    return p.h32 ? a * s_rstd[t] : a;  // fused RMSNorm: the per-token scale factored out of the dot product
   };
   if (!p.swiglu) {
     const int row0 = ub * GV_UR, n_rows = min(n_units * GV_UR, p.F - row0);
@@ -283,6 +362,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_kernel(const __grid_consta
       reinterpret_cast<__half*>(p.out)[(long long)t * p.ldo + ub * GV_UR + u] = __float2half_rn(silu_f(a) * b);
     }
   }
+  if (p.trace && tid == 0) p.trace[blockIdx.x * 6 + 5] = gv_time();  // epilogue done
 }
 
 }  // namespace myr
@@ -301,12 +381,14 @@ int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream) {
   p.out = a->out; p.out_dtype = a->out_dtype; p.ldo = a->ldo;
   p.swiglu = a->act == MYR_ACT_SWIGLU;
   p.w_static = a->w_static;
+  p.trace = next_trace_slot();
   p.n_kc = ceil_div(a->K, GV_SK);
   p.kp = ceil_div(a->K, GV_WK) * GV_WK;
+  MYR_CHECK_ARG(p.n_kc <= GV_MAX_KC, "gemm: K=%d exceeds the small-batch path (K <= %d)", a->K, GV_MAX_KC * GV_SK);
   if (p.h32) {
-    MYR_CHECK_ARG(p.gamma != nullptr && a->K % 4 == 0 && a->K <= GV_NORM_VEC * 4 * GV_CTHREADS && a->norm_ldh % 4 == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.h32) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.gamma) & 15) == 0,
-                  "gemm: fused RMSNorm needs K %% 4 == 0, K <= %d and 16-byte aligned fp32 rows", GV_NORM_VEC * 4 * GV_CTHREADS);
+    MYR_CHECK_ARG(p.gamma != nullptr && a->norm_ldh % 4 == 0 && (reinterpret_cast<uintptr_t>(p.h32) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.gamma) & 15) == 0,
+                  "gemm: fused RMSNorm needs 16-byte aligned fp32 rows");
   }
   // weights as a 3-D tensor: (64 k, F rows, K / 64 k-blocks); one box = 64 x 8 rows x 8 k-blocks = 8 KiB, 128-byte swizzled
   CUtensorMap tmW;
@@ -325,9 +407,18 @@ int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream) {
     if (grid > p.units) grid = p.units;
     const int upc = ceil_div(p.units, grid);
     p.max_groups = p.swiglu ? upc : (upc + 1) / 2;
-    const size_t red_bytes = (size_t)GV_CWARPS * p.max_groups * 32 * sizeof(float4);
-    const size_t fixed = x_bytes + red_bytes + GV_CWARPS * GV_T * 4 + 2 * GV_MAX_STAGES * 8 + 1024;
-    int stages = (int)(((long long)GV_SMEM_BUDGET - (long long)fixed) / GV_STAGE_BYTES);
+    const size_t red_bytes = (size_t)GV_CWARPS * p.max_groups * 16 * sizeof(float4);
+    const size_t fixed = x_bytes + red_bytes + (p.h32 ? GV_HBUF_BYTES : 0) + GV_CWARPS * GV_T * 4 + (2 * GV_MAX_STAGES + GV_MAX_KC + 2) * 8 +
+                         GV_T * 4 + 1024;
+    // leave ~8 KB of the SM's shared memory to a small co-resident CTA of the next kernel (decode attention pre-loads its K rows
+    // while this kernel streams) unless that would cost a ring stage of an already shallow ring
+    static long long budget = -1;
+    if (budget < 0) {
+      const char* e = getenv("MYR_GEMV_SMEM_KB");
+      budget = e ? atoll(e) * 1024 : (long long)GV_SMEM_BUDGET - 8192;
+    }
+    int stages = (int)((budget - (long long)fixed) / GV_STAGE_BYTES);
+    if (stages < 4) stages = (int)(((long long)GV_SMEM_BUDGET - (long long)fixed) / GV_STAGE_BYTES);
     if (stages > GV_MAX_STAGES) stages = GV_MAX_STAGES;
     if (stages >= 3 || (stages >= 2 && grid == p.units)) {
       p.stages = stages;

@@ -14,11 +14,11 @@ from myriad_b200 import kernels as K
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 B = 4
-# decode weight-streaming GEMMs (T = 4) in layer order: qkv (+LoRA A rows), o (+res), gate/up (+SwiGLU), down (+res);
+# decode weight streaming (T = 4, gemv_kernel) in layer order: norm+qkv (+LoRA A rows), o (+res), norm+gate/up (+SwiGLU), down (+res);
 # fresh weights per launch (no L2 reuse)
 x = torch.randn(B, 4096, device=dev).half()
 a = torch.randn(B, 11008, device=dev).half()
-res = torch.zeros(B, 4096, device=dev)
+res = torch.randn(B, 4096, device=dev)
 qkv = torch.empty(B, 12304, device=dev, dtype=torch.float16)
 act = torch.empty(B, 11008, device=dev, dtype=torch.float16)
 for i in range(2):
@@ -26,9 +26,10 @@ for i in range(2):
     wo = (torch.randn(4096, 4096, device=dev) * 0.02).half()
     wgu = (torch.randn(22016, 4096, device=dev) * 0.02).half()
     wd = (torch.randn(4096, 11008, device=dev) * 0.02).half()
-    K.gemm(x, wq, out=qkv, w_static=True)
+    gamma = torch.ones(4096, device=dev)
+    K.gemm(None, wq, out=qkv, w_static=True, norm=(res, gamma, 1e-6))  # small-batch kernel (gemv.cu), fused RMSNorm prologue
     K.gemm(x, wo, res=res, out=res, w_static=True)
-    K.gemm(x, wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
+    K.gemm(None, wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm=(res, gamma, 1e-6))
     K.gemm(a, wd, res=res, out=res, w_static=True)
 # ViT GEMMs at the bench batch (T = 4 * 257): qkv, fc1 + GELU, fc2 + residual
 T = B * 257
