@@ -815,8 +815,8 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
     MYR_CHECK_ARG((a->res == nullptr || (a->ldr > 0)) && a->ldo > 0, "gemm: bad leading dimensions");
     return myr_gemv_dispatch(a, stream);
   }
-  if (a->norm_h32 != nullptr) {
-    set_error("gemm: the fused RMSNorm prologue exists on the small-batch path only (T <= 4, plain K-major operands, no hints)");
+  if (a->norm_h32 != nullptr || a->norm_ss != nullptr || a->post_out16 != nullptr) {
+    set_error("gemm: the fused RMSNorm prologue / hand-over exists on the small-batch path only (T <= 4, plain K-major operands, no hints)");
     return MYR_ERR_UNSUPPORTED;
   }
 

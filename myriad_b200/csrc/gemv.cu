@@ -50,6 +50,8 @@ struct GemvParams {
   const __half* x; long long ldx;                 // fp16 activations [T, K] ...
   const float* h32; long long ldh;                // ... or the fp32 residual stream to RMS-normalise on the fly
   const float* gamma; float eps;
+  const float* in_ss;                             // ... or x was pre-scaled by the producer (post_*) and only the RMSNorm scale is missing
+  const float* post_gamma; __half* post16; long long post_ld; float* post_ss;  // producer side of that hand-over
   const __half* bias;
   const void* res; int res_dtype; long long ldr;
   void* out; int out_dtype; long long ldo;
@@ -183,6 +185,19 @@ __global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap 
           for (int t = 0; t < p.T; ++t)
             bulk_g2s(smem_u32(xs + (size_t)t * xld + k0), p.x + (long long)t * p.ldx + k0, bytes, smem_u32(&xbar[kc]));
         }
+      }
+      if (p.in_ss) {
+        // RMSNorm scale from the producer's per-CTA sums of squares (summed in CTA order: deterministic); needed by the
+        // epilogue only, so its latency is off the critical path
+        if (stid != 0) pdl_wait();
+        if (stid < GV_T) {
+          const int parts = (int)__ldcg(p.in_ss);
+          float tot = 0.f;
+          for (int c = 0; c < parts; ++c) tot += __ldcg(p.in_ss + 4 + c * GV_T + stid);
+          s_rstd[stid] = rsqrtf(tot / p.K + p.eps);
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(GV_STHREADS) : "memory");
+        if (stid == 0) mbar_arrive(rbar);
       }
     } else {
       // LlamaRMSNorm (modeling_llama.py:66-74): x = h * rsqrt(mean(h^2) + eps) * gamma. The per-token scale is a scalar, so
@@ -322,7 +337,7 @@ __global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap 
       ++kc;
     }
   }
-  if (p.h32) mbar_wait(rbar, 0);
+  if (p.h32 || p.in_ss) mbar_wait(rbar, 0);
   consumer_sync();
   if (p.trace && tid == 0 && !p.h32) p.trace[blockIdx.x * 6 + 4] = gv_time();  // last stage consumed
 
@@ -334,10 +349,11 @@ __global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap 
     float a = 0.f;
 #pragma unroll
     for (int w = 0; w < GV_CWARPS; ++w) a += redf[(((size_t)w * p.max_groups + gg) * 16 + l) * 4 + j];
-    return p.h32 ? a * s_rstd[t] : a;  // fused RMSNorm: the per-token scale factored out of the dot product
+    return (p.h32 || p.in_ss) ? a * s_rstd[t] : a;  // fused RMSNorm: the per-token scale factored out of the dot product
   };
   if (!p.swiglu) {
     const int row0 = ub * GV_UR, n_rows = min(n_units * GV_UR, p.F - row0);
+    float ssq = 0.f;  // this thread's token is tid % GV_T in every iteration (GV_CTHREADS is a multiple of GV_T)
     for (int i = tid; i < n_rows * GV_T; i += GV_CTHREADS) {
       const int u = i / GV_T, t = i % GV_T;
       if (t >= p.T) continue;
@@ -352,6 +368,23 @@ __global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap 
         reinterpret_cast<float*>(p.out)[(long long)t * p.ldo + row] = a;
       else
         reinterpret_cast<__half*>(p.out)[(long long)t * p.ldo + row] = __float2half_rn(a);
+      if (p.post16) {
+        // hand-over to the next projection's RMSNorm: its activations without the per-token scale, and this slice's sum of squares
+        p.post16[(long long)t * p.post_ld + row] = __float2half_rn(a * p.post_gamma[row]);
+        ssq = fmaf(a, a, ssq);
+      }
+    }
+    if (p.post16) {
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);  // lanes with the same token
+      if (lane < GV_T) s_part[warp * GV_T + lane] = ssq;
+      consumer_sync();
+      if (tid < GV_T) {
+        float tot = 0.f;
+        for (int w = 0; w < GV_CWARPS; ++w) tot += s_part[w * GV_T + tid];
+        p.post_ss[4 + blockIdx.x * GV_T + tid] = tot;
+        if (blockIdx.x == 0 && tid == 0) p.post_ss[0] = (float)gridDim.x;
+      }
     }
   } else {
     // SwiGLU (modeling_llama.py:139-140) with the rounding points of the unfused path: gate / up rounded to fp16 first
@@ -376,6 +409,13 @@ int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream) {
   p.x = reinterpret_cast<const __half*>(a->x); p.ldx = a->ldx;
   p.h32 = reinterpret_cast<const float*>(a->norm_h32); p.ldh = a->norm_ldh;
   p.gamma = reinterpret_cast<const float*>(a->norm_gamma); p.eps = a->norm_eps;
+  p.in_ss = reinterpret_cast<const float*>(a->norm_ss);
+  p.post_gamma = reinterpret_cast<const float*>(a->post_gamma);
+  p.post16 = reinterpret_cast<__half*>(a->post_out16); p.post_ld = a->post_ld;
+  p.post_ss = reinterpret_cast<float*>(a->post_ss);
+  MYR_CHECK_ARG(!(p.in_ss && p.h32), "gemm: norm_h32 and norm_ss are alternatives");
+  MYR_CHECK_ARG(p.post16 == nullptr || (p.post_gamma && p.post_ss && !(a->act == MYR_ACT_SWIGLU) && a->post_ld > 0),
+                "gemm: post_out16 needs post_gamma, post_ss, a row stride and a plain (non-SwiGLU) epilogue");
   p.bias = reinterpret_cast<const __half*>(a->bias);
   p.res = a->res; p.res_dtype = a->res_dtype; p.ldr = a->ldr;
   p.out = a->out; p.out_dtype = a->out_dtype; p.ldo = a->ldo;

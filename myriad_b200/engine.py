@@ -337,7 +337,7 @@ class MyriadEngine:
             self.vcache = torch.zeros_like(self.kcache)
             self._decode_graphs = {}
 
-    def _llama_layer(self, L, li, h32, bufs, B, S, pos, kv_len, cache_off, cache_off_dev, Skv, causal):
+    def _llama_layer(self, L, li, h32, bufs, B, S, pos, kv_len, cache_off, cache_off_dev, Skv, causal, hand=None, next_gamma=None):
         """LlamaDecoderLayer.forward modeling_llama.py:247-299 as 8 launches: RMSNorm -> qkv (+ LoRA A rows) GEMM -> RoPE +
         LoRA B + KV-cache append -> flash attention -> o_proj GEMM (+ residual) -> RMSNorm -> gate/up GEMM with fused
         SwiGLU -> down GEMM (+ residual). Weights are static, so each GEMM may prefetch them under the previous kernel."""
@@ -349,7 +349,12 @@ class MyriadEngine:
         # T <= 4 (greedy decode at the reference's batch sizes): the small-batch weight-streaming kernel computes the RMSNorm
         # in its own prologue, so a layer is 5 dependent launches instead of 7
         fuse = T <= 4 and self.fuse_small_batch_norm
-        if fuse:
+        # decode steps also hand the RMSNorm over between launches: o_proj / down_proj write rn_f16(h * gamma_next) and their
+        # slice's sum of squares next to the fp32 stream, the next projection copies those rows and only applies the scale
+        hand = hand if fuse else None
+        if hand is not None and li > 0:
+            K.gemm(hand.yb, L.wqkv, out=qkv, w_static=True, norm_ss=(hand.ssb, l.eps))
+        elif fuse:
             K.gemm(None, L.wqkv, out=qkv, w_static=True, norm=(h32, L.n1, l.eps))
         else:
             K.norm(h32, L.n1, None, l.eps, rms=True, out16=x16)
@@ -366,6 +371,11 @@ class MyriadEngine:
             cs = (kc.stride(1), kc.stride(0), dh)
             K.attention(qkv, kc, vc, ctx, B, H, S, Skv, dh, 1.0 / math.sqrt(dh), (ldq, S * ldq, dh), cs, cs, (D, S * D, dh),
                         causal=causal, q_off=0, kv_len=kv_len)
+        if hand is not None:
+            K.gemm(ctx, L.wo, res=h32, out=h32, w_static=True, post_norm=(L.n2, hand.ya, hand.ssa))
+            K.gemm(hand.ya, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm_ss=(hand.ssa, l.eps))
+            K.gemm(act, L.wd, res=h32, out=h32, w_static=True, post_norm=(next_gamma, hand.yb, hand.ssb))
+            return
         K.gemm(ctx, L.wo, res=h32, out=h32, w_static=True)
         if fuse:
             K.gemm(None, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm=(h32, L.n2, l.eps))
@@ -409,9 +419,13 @@ class MyriadEngine:
         l = self.d.llama
         B = st.B
         K.embed(self.llw.embed, st.cur_tok, st.h32)
+        hand = st.hand if (B <= 4 and self.fuse_small_batch_norm) else None
         for li, L in enumerate(self.llw.layers):
-            self._llama_layer(L, li, st.h32, st.bufs, B, 1, st.pos, st.kv_len, 0, st.cache_off, st.Skv, False)
-        if B <= 4 and self.fuse_small_batch_norm:
+            nxt = self.llw.layers[li + 1].n1 if li + 1 < l.layers else self.llw.norm
+            self._llama_layer(L, li, st.h32, st.bufs, B, 1, st.pos, st.kv_len, 0, st.cache_off, st.Skv, False, hand=hand, next_gamma=nxt)
+        if hand is not None:
+            K.gemm(hand.yb, self.llw.lm_head, out=st.logits, w_static=True, norm_ss=(hand.ssb, l.eps))
+        elif B <= 4 and self.fuse_small_batch_norm:
             K.gemm(None, self.llw.lm_head, out=st.logits, w_static=True, norm=(st.h32, self.llw.norm, l.eps))
         else:
             K.norm(st.h32, self.llw.norm, None, l.eps, rms=True, out16=st.bufs[0])
@@ -471,6 +485,9 @@ class MyriadEngine:
         st.h32 = torch.empty(B, l.hidden, device=dev, dtype=F32)
         st.bufs = self._llama_bufs(B)
         st.logits = torch.empty(B, l.vocab, device=dev, dtype=F32)
+        st.hand = _Obj()  # RMSNorm hand-over buffers of the small-batch path (o_proj -> gate/up, down_proj -> next qkv / lm_head)
+        st.hand.ya, st.hand.yb = (torch.zeros(B, l.hidden, device=dev, dtype=F16) for _ in range(2))
+        st.hand.ssa, st.hand.ssb = (torch.zeros(K.NORM_SS_FLOATS, device=dev, dtype=F32) for _ in range(2))
         st.graph = None
         st.mega = self._mega_plan(st) if self._mega_ok(B, Skv) else None
         return st

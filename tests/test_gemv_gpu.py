@@ -170,3 +170,27 @@ def test_gemv_dependent_chain_in_cuda_graph(K):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(h, eager), "graph replay must equal the eager launches exactly"
+
+
+def test_gemv_rmsnorm_hand_over(K, O):
+    """o_proj-style producer writes rn_f16(h * gamma) + per-CTA sums of squares; the consumer multiplies by the scale in its
+    epilogue: == RMSNorm(h) @ W^T of the oracle (modeling_llama.py:66-74), and == the in-kernel fused-norm path."""
+    T, D, F = 4, 4096, 12304
+    ctx = rnd(T, D, seed=1).half().to(dev())
+    wo = (rnd(D, D, seed=2) / D ** 0.5).half().to(dev())
+    h0 = rnd(T, D, seed=3, std=2.0).to(dev())
+    gamma = (1.0 + 0.1 * rnd(D, seed=4)).to(dev())
+    w = (rnd(F, D, seed=5) / D ** 0.5).half().to(dev())
+    h = h0.clone()
+    y16 = torch.zeros(T, D, device=dev(), dtype=torch.float16)
+    ss = torch.zeros(K.NORM_SS_FLOATS, device=dev(), dtype=torch.float32)
+    K.gemm(ctx, wo, res=h, out=h, w_static=True, post_norm=(gamma, y16, ss))
+    y = K.gemm(y16, w, out_dtype=torch.float32, w_static=True, norm_ss=(ss, 1e-6))
+    href = h0.cpu() + ctx.float().cpu() @ wo.float().cpu().t()
+    close(h, href, 1e-3, "producer output")
+    assert int(ss[0].item()) >= 1
+    tot = ss[4:4 + 4 * int(ss[0].item())].reshape(-1, 4).sum(0).cpu()
+    close(tot, href.pow(2).sum(-1), 1e-4, "sum of squares partials")
+    close(y, O.rms_norm(href, gamma.cpu(), 1e-6) @ w.float().cpu().t(), 2e-3, "hand-over vs oracle")
+    y2 = K.gemm(None, w, norm=(h, gamma, 1e-6), out=torch.empty(T, F, device=dev(), dtype=torch.float32), w_static=True)
+    close(y, y2, 5e-4, "hand-over vs in-kernel norm")
