@@ -252,8 +252,8 @@ def run_train_leg(args, dims, dev, world, rank, barrier):
 def roofline_probe(eng, dims, dev, peaks):
     """Dominant kernel = the small-batch weight-streaming kernel (csrc/gemv.cu, `gemv_kernel`): ~75 % of a step is the 32
     decode steps, each streaming every LLaMA weight once through 4 launches per layer. Timed live with CUDA events over the
-    real 32 layers' weights in layer order and in the decode step's own launch configuration (fused RMSNorm prologues,
-    in-place fp32 residual, SwiGLU epilogue; 13 GB >> L2, so nothing is re-served from cache). Also reports the tensor-bound
+    real 32 layers' weights in layer order and in the decode step's own launch configuration (RMSNorm hand-over, in-place
+    fp32 residual, SwiGLU epilogue; 13 GB >> L2, so nothing is re-served from cache). Also reports the tensor-bound
     ViT GEMM for context."""
     import torch
 
@@ -268,18 +268,21 @@ def roofline_probe(eng, dims, dev, peaks):
     act = torch.empty(B, l.inter, device=dev, dtype=torch.float16)
     fused = eng.fuse_small_batch_norm and B <= 4
 
+    ya, yb = (torch.zeros(B, l.hidden, device=dev, dtype=torch.float16) for _ in range(2))
+    ssa, ssb = (torch.zeros(K.NORM_SS_FLOATS, device=dev) for _ in range(2))
+
     def sweep():
         for L in eng.llw.layers:
-            if fused:
-                K.gemm(None, L.wqkv, out=qkv, w_static=True, norm=(o, L.n1, l.eps))
+            if fused:  # the decode step's own launch configuration: RMSNorm handed over between the projections
+                K.gemm(yb, L.wqkv, out=qkv, w_static=True, norm_ss=(ssb, l.eps))
+                K.gemm(x, L.wo, res=o, out=o, w_static=True, post_norm=(L.n2, ya, ssa))
+                K.gemm(ya, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm_ss=(ssa, l.eps))
+                K.gemm(a, L.wd, res=o, out=o, w_static=True, post_norm=(L.n1, yb, ssb))
             else:
                 K.gemm(x, L.wqkv, out=qkv, w_static=True)
-            K.gemm(x, L.wo, res=o, out=o, w_static=True)
-            if fused:
-                K.gemm(None, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm=(o, L.n2, l.eps))
-            else:
+                K.gemm(x, L.wo, res=o, out=o, w_static=True)
                 K.gemm(x, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
-            K.gemm(a, L.wd, res=o, out=o, w_static=True)
+                K.gemm(a, L.wd, res=o, out=o, w_static=True)
 
     for _ in range(2):
         sweep()
@@ -295,9 +298,9 @@ def roofline_probe(eng, dims, dev, peaks):
     ms = e0.elapsed_time(e1) / reps
     n_launch = 4 * l.layers
     wbytes = l.layers * 2 * (wq * l.hidden + l.hidden * l.hidden + 2 * l.inter * l.hidden + l.hidden * l.inter)
-    # activations per layer: the two normed projections read the fp32 residual rows + gamma, o / down read fp16 rows and read +
-    # write the fp32 residual; qkv / act are written in fp16
-    abytes = l.layers * (2 * (B * 4 * l.hidden + 4 * l.hidden) + B * 2 * l.hidden + B * 2 * l.inter + 2 * 2 * B * 4 * l.hidden +
+    # activations per layer: fp16 rows in (3 x hidden + inter), fp32 residual read + written by o / down, their fp16 hand-over
+    # rows + gamma, qkv / act written in fp16
+    abytes = l.layers * (B * 2 * (3 * l.hidden + l.inter) + 2 * 2 * B * 4 * l.hidden + 2 * (B * 2 * l.hidden + 4 * l.hidden) +
                          B * 2 * wq + B * 2 * l.inter)
     per_launch = (wbytes + abytes) / n_launch
     achieved = (wbytes + abytes) / (ms / 1e3) / 1e9

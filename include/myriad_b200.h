@@ -83,21 +83,17 @@ typedef struct {
   int32_t alpha_set; float alpha; /* if alpha_set: v *= alpha (fp32, unrounded) after the activation, before the residual add */
   int32_t pdl;                 /* launch with programmatic stream serialization (overlaps the previous kernel's tail) */
   int32_t w_static;            /* w is not written by any kernel in flight: its tiles may be prefetched before the PDL wait */
-  /* Optional fused LlamaRMSNorm prologue (modeling_llama.py:66-74), small-batch path only (T <= 4, see below): when
-   * norm_h32 != NULL, x is ignored and the activations are rn_f16(h * rsqrt(mean(h^2) + norm_eps) * norm_gamma) computed from
-   * the fp32 rows norm_h32[t * norm_ldh + k] (k < K <= 4096) by every CTA itself. MYR_ERR_UNSUPPORTED if T > 4. */
-  const void* norm_h32; int64_t norm_ldh; const void* norm_gamma; float norm_eps;
   /* Hand-over of an RMSNorm between two small-batch launches (T <= 4), so that the second one does not have to read and
    * normalise the fp32 stream on its critical path. Producer (the projection whose output + residual IS the stream, e.g.
    * o_proj / down_proj): post_out16[t * post_ld + f] = rn_f16(out[t, f] * post_gamma[f]) and post_ss = { n_parts, -, -, -,
-   * per-CTA sums of out[t, f]^2 [n_parts][4] } (post_ss must hold 4 + 4 * 148 floats). Consumer: x = post_out16 and
+   * sums of out[t, f]^2 over each block of 8 features [n_parts][4] } (post_ss must hold 4 + F / 2 floats). Consumer: x = post_out16 and
    * norm_ss = post_ss (+ norm_eps): the result is multiplied by rsqrt(sum / K + eps) per token in the epilogue. */
   const void* post_gamma; void* post_out16; int64_t post_ld; void* post_ss;
-  const void* norm_ss;
+  const void* norm_ss; float norm_eps;
 } myr_gemm_args;
-/* Small-batch path: T <= 4 with K-major fp16 operands, act NONE or SWIGLU and no scale_cols / round_acc / alpha / row
- * groups / batch / hints runs on a CUDA-core weight-streaming kernel (csrc/gemv.cu: one CTA per SM owns whole output rows,
- * no split tiles, no workspace). myr_set_gemv(0) (or env MYR_GEMV=0) routes those shapes to the tcgen05 kernel instead;
+/* Small-batch path: T <= 4 with K-major fp16 operands, K % 128 == 0, act NONE or SWIGLU and no scale_cols / round_acc / alpha /
+ * row groups / batch / hints runs on the weight-streaming kernel of csrc/gemv.cu (row groups of 16 output rows reduced inside
+ * one CTA: no split tiles; the last int of the workspace's counter area hands out row groups, zero on entry and on exit). myr_set_gemv(0) (or env MYR_GEMV=0) routes those shapes to the tcgen05 kernel instead;
  * returns the previous setting. */
 int32_t myr_set_gemv(int32_t enabled);
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);

@@ -738,7 +738,7 @@ static Plan make_plan(const myr_gemm_args* a, int nbatch, bool allow_split, size
   if (want_split && nbatch == 1) {
     const int max_seg = (pl.kb_total + per - 1) / per + 1;
     const size_t need = (size_t)pl.n_tiles * max_seg * pl.BN * BM;
-    if (pl.n_tiles <= MAX_COUNTERS && need <= ws_floats) {
+    if (pl.n_tiles < MAX_COUNTERS && need <= ws_floats) {
       pl.per = per;
       pl.grid = (int)((pl.total_kb + per - 1) / per);
       pl.max_seg = max_seg;
@@ -768,7 +768,7 @@ extern "C" size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K) {
   return COUNTER_BYTES + tiles * 4 * 256 * BM * sizeof(float);
 }
 
-int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream);  // gemv.cu
+int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter);  // gemv.cu
 
 static int g_gemv = -1;  // < 0: not read from the environment yet
 static int gemv_enabled() {
@@ -813,10 +813,14 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
   }
   if (gemv_enabled() && gemv_eligible(a, nbatch)) {
     MYR_CHECK_ARG((a->res == nullptr || (a->ldr > 0)) && a->ldo > 0, "gemm: bad leading dimensions");
-    return myr_gemv_dispatch(a, stream);
+    // the last arrival counter of the workspace head hands out row groups (zero on entry, left at zero)
+    int* ctr = nullptr;
+    if (a->workspace != nullptr && a->workspace_bytes >= COUNTER_BYTES && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0)
+      ctr = reinterpret_cast<int*>(a->workspace) + (MAX_COUNTERS - 1);
+    return myr_gemv_dispatch(a, stream, ctr);
   }
-  if (a->norm_h32 != nullptr || a->norm_ss != nullptr || a->post_out16 != nullptr) {
-    set_error("gemm: the fused RMSNorm prologue / hand-over exists on the small-batch path only (T <= 4, plain K-major operands, no hints)");
+  if (a->norm_ss != nullptr || a->post_out16 != nullptr) {
+    set_error("gemm: the RMSNorm hand-over exists on the small-batch path only (T <= 4, plain K-major operands, no hints)");
     return MYR_ERR_UNSUPPORTED;
   }
 

@@ -6,19 +6,26 @@
 // fix-up through global memory (32 weight tiles of 128 rows do not fill 148 SMs without splitting K) and a separate
 // RMSNorm launch in front of it: ~45 of 113 us per layer with the HBM idle (profiles/r1_decode_timeline.md).
 // This kernel removes those phases instead of hiding them:
-//   * one CTA per SM owns a contiguous slice of OUTPUT ROWS (balanced to 8 rows), so a row's whole K range is reduced
-//     inside the CTA: no split tiles, no workspace, no atomics, no fix-up;
+//   * the unit of work is an ITEM of 8 output rows (SwiGLU: 8 gate/up pairs) x the whole K range, reduced entirely inside one
+//     CTA: no split tiles, no partial tiles in global memory, no fix-up. One CTA per SM takes ~3/4 of its share of the items
+//     by index and the rest from an atomic counter, because SMs do not stream equally fast (the first and the last CTA of a
+//     statically balanced launch finish 2-7 us apart on B200);
 //   * a producer thread streams weights with TMA through a 3-D view of W (64 k, rows, K/64): one 8 KiB box = 8 rows x 512 k,
-//     128-byte swizzled, into a ring of up to 6 stages x 32 KiB (128-192 KB in flight per SM, evict-first in L2, filled
-//     before the PDL wait because weights are static). (16-byte cp.async tops out at ~4.2 TB/s, 1-D bulk copies of 2 KiB
-//     rows at ~4.4 TB/s on B200; 8 KiB tensor boxes keep the TMA engine's per-instruction cost off the critical path.)
-//   * the 4 x K activation block lives in shared memory as fp16; for the projections that follow an RMSNorm
-//     (modeling_llama.py:66-74: q/k/v, gate/up, lm_head) the CTA computes the norm itself from the fp32 residual stream,
-//     which removes the norm launches from the dependent chain;
+//     128-byte swizzled, into a ring of 16 / 32 KiB stages (128-192 KB in flight per SM, evict-first in L2; the
+//     items assigned by index are requested before the PDL wait because weights are static). (16-byte cp.async tops
+//     out at ~4.2 TB/s, 1-D bulk copies of 2 KiB rows at ~4.4 TB/s on B200; 8 KiB tensor boxes reach 6.9 TB/s.)
+//   * the 4 x K activation block comes in by TMA bulk copy, one 1024-k chunk per mbarrier, so the first group starts on
+//     chunk 0 while the rest is in flight (global loads issued under a saturated TMA stream take 2-3 us per round trip;
+//     TMA transfers do not queue behind it);
 //   * 8 consumer warps split each 1024-k stage; mma.sync.m16n8k16 (A = 16 weight rows via ldmatrix, B = the activation rows,
-//     fp32 accumulate) does the dot products, so no shuffles; warps are summed in fixed order (deterministic, CUDA-graph
-//     replay == eager). tcgen05 would need a TMEM drain per 16 rows and buys nothing at 2 flop/byte;
-//   * epilogues: bias, fp16/fp32 residual (in place), fp16/fp32 store, SwiGLU over 64-row interleaved gate/up weights.
+//     fp32 accumulate in registers over the k stages of a group) does the dot products; the 8 warps' partial sums meet in
+//     shared memory once per group and are added in warp order (deterministic, CUDA-graph replay == eager). tcgen05 would
+//     need a TMEM drain per 16 rows and buys nothing at 2 flop/byte;
+//   * epilogue per group: bias, fp16/fp32 residual (in place), fp16/fp32 store, SwiGLU over 64-row interleaved gate/up
+//     weights; LlamaRMSNorm (modeling_llama.py:66-74) in front of q/k/v, gate/up and lm_head is split between two launches:
+//     the projection that produces the fp32 stream (o_proj / down_proj) also writes rn_f16(h * gamma_next) and each item's sum
+//     of squares (post_*), the consumer multiplies its dot products by rsqrt(sum / K + eps) (norm_ss) - the scale is a
+//     per-token scalar and the projection is linear in x, so no norm launch sits in the dependent chain.
 // Replaces, for T <= 4: nn.Linear of q/k/v/o/gate/up/down/lm_head (modeling_llama.py:139-140,168-231,629-716) + peft LoRA-A
 // rows riding on the qkv weight (myriad.py:171-178) + LlamaRMSNorm in front of them.
 #include "common.h"
@@ -28,37 +35,33 @@ namespace myr {
 
 constexpr int GV_CWARPS = 8;                      // consumer (MMA) warps
 constexpr int GV_CTHREADS = GV_CWARPS * 32;
-constexpr int GV_SWARPS = 2;                      // activation-staging warps
-constexpr int GV_STHREADS = GV_SWARPS * 32;
-constexpr int GV_THREADS = GV_CTHREADS + 32 + GV_STHREADS;  // consumers + one producer warp (TMA issue) + stagers
-constexpr int GV_MAX_KC = 32;                     // k stages per row: K <= 32768
-constexpr int GV_HK = 512;                        // k per TMA transfer of the fp32 residual rows (fused RMSNorm)
-constexpr int GV_HBUF_BYTES = (4 + 1) * GV_HK * 4;  // GV_T rows + the gamma slice: 10 KiB
-constexpr int GV_UR = 8;                          // weight rows per unit = rows of one TMA box
+constexpr int GV_THREADS = GV_CTHREADS + 64;      // + producer warp (weight TMA) + stager warp (activation TMA, norm scale)
+constexpr int GV_MAX_KC = 32;                     // k stages per row group: K <= 32768
 constexpr int GV_T = 4;                           // activation rows held in shared memory (the N side holds 8; rows >= T are zero)
 constexpr int GV_WK = 128;                        // k elements per consumer warp and stage
 constexpr int GV_SK = GV_CWARPS * GV_WK;          // k elements per stage (1024)
 constexpr int GV_BOX_K = 512;                     // k elements per TMA box: 8 k-blocks of 64 halfs (one 128-byte swizzle row each)
-constexpr int GV_BOX_BYTES = GV_UR * GV_BOX_K * 2;  // 8 KiB
+constexpr int GV_BOX_BYTES = 8 * GV_BOX_K * 2;    // 8 rows: 8 KiB
 constexpr int GV_STAGE_BYTES = 4 * GV_BOX_BYTES;  // 16 rows x 1024 k: boxes [k half][row half]
 constexpr int GV_MAX_STAGES = 6;
 constexpr int GV_SMEM_BUDGET = 227 * 1024;        // max dynamic shared memory per CTA on sm_100
 constexpr int GV_XPAD = 8;                        // halfs of padding per activation row (bank spread)
+constexpr int GV_RED_FLOATS = GV_CWARPS * 16 * 4; // one work item's D fragments: [warp][16 lanes][4]
 
 struct GemvParams {
   int F, K, T;
-  const __half* x; long long ldx;                 // fp16 activations [T, K] ...
-  const float* h32; long long ldh;                // ... or the fp32 residual stream to RMS-normalise on the fly
-  const float* gamma; float eps;
-  const float* in_ss;                             // ... or x was pre-scaled by the producer (post_*) and only the RMSNorm scale is missing
+  const __half* x; long long ldx;                 // fp16 activations [T, K]
+  const float* in_ss; float eps;                  // optional: x lacks the RMSNorm scale; per-CTA sums of squares of its producer
   const float* post_gamma; __half* post16; long long post_ld; float* post_ss;  // producer side of that hand-over
   const __half* bias;
   const void* res; int res_dtype; long long ldr;
   void* out; int out_dtype; long long ldo;
   int swiglu;
-  int units;                                      // 8-row units in total (SwiGLU: units of 8 gate/up pairs = 8 + 8 rows)
+  int n_units;                                    // units in total: 8 output rows (SwiGLU: 8 gate/up pairs = 8 + 8 weight rows)
+  int gsz;                                        // units per MMA row group: 2 (plain: 16 rows) or 1 (SwiGLU)
+  int u_static;                                   // units [0, u_static) are split evenly by CTA index, the rest go through `counter`
+  int* counter;                                   // zero on entry, left at zero (null: u_static == n_units)
   int n_kc, kp;                                   // k stages per row group = ceil(K / 1024), K padded to 128
-  int max_groups;                                 // row groups of the largest CTA slice (sizes the partial-sum buffer)
   int stages;
   int w_static;
   long long* trace;                               // debug: 6 x %globaltimer ns per CTA (myr_gemm_set_trace)
@@ -85,13 +88,13 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GV_CTHREADS) : "memory"); }
 
-// A row group is 16 weight rows = two 8-row halves, each one TMA box per 512 k:
-//   plain  : group g of the slice = units ub + 2g (rows 0..7) and ub + 2g + 1 (rows 8..15, absent in an odd tail)
-//   SwiGLU : group g = unit ub + g: rows 0..7 = gate rows of pairs 8(ub+g) .. +7, rows 8..15 = the matching up rows
+// first weight row of the low (rows 0..7) / high (rows 8..15) 8-row box of the row group that starts at unit u0:
+//   plain  : units u0 (low) and u0 + 1 (high; absent in a one-unit group): rows 8 u0 .. 8 u0 + 15
+//   SwiGLU : low = gate rows of pairs 8 u0 .. 8 u0 + 7, high = the matching up rows
 //            (weights interleaved in blocks of 64: [gate 0..63 | up 0..63 | gate 64..127 | ...])
-__device__ __forceinline__ int gv_half_row0(const GemvParams& p, int ub, int n_units, int g, int half) {
-  if (!p.swiglu) return (2 * g + half < n_units) ? (ub + 2 * g + half) * GV_UR : -1;
-  const int i0 = (ub + g) * GV_UR;
+__device__ __forceinline__ int gv_half_row0(const GemvParams& p, int u0, int half) {
+  if (!p.swiglu) return (u0 + half) * 8;
+  const int i0 = u0 * 8;
   return ((i0 >> 6) << 7) + (i0 & 63) + (half << 6);
 }
 
@@ -99,33 +102,26 @@ __global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // balanced contiguous slices of 8-row units: sizes differ by at most one
-  const int ub = (int)(((long long)blockIdx.x * p.units) / gridDim.x);
-  const int n_units = (int)(((long long)(blockIdx.x + 1) * p.units) / gridDim.x) - ub;
-  const int n_groups = p.swiglu ? n_units : (n_units + 1) / 2;
-  const int n_it = n_groups * p.n_kc;                     // iteration = (row group outer, k stage inner): 16 rows x 1024 k
   const int xld = p.kp + GV_XPAD;
 
   uint8_t* ring = smem;
   __half* xs = reinterpret_cast<__half*>(ring + (size_t)p.stages * GV_STAGE_BYTES);       // [GV_T][xld]
-  float* s_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)GV_T * xld * 2);  // [warps][GV_T]
-  float4* red = reinterpret_cast<float4*>(s_part + GV_CWARPS * GV_T);                       // [warps][max_groups][16 lanes]
-  float* hbuf = reinterpret_cast<float*>(red + (size_t)GV_CWARPS * p.max_groups * 16);      // [GV_T][GV_HK] fp32 (fused RMSNorm only)
-  uint64_t* full = reinterpret_cast<uint64_t*>(hbuf + (p.h32 ? (GV_T + 1) * GV_HK : 0));          // [stages] producer -> consumers
-  uint64_t* empty = full + GV_MAX_STAGES;                                                     // [stages] consumers -> producer
-  uint64_t* xbar = empty + GV_MAX_STAGES;                                                     // [n_kc] activation chunk kc staged
-  uint64_t* rbar = xbar + GV_MAX_KC;                                                          // RMSNorm scale ready
-  uint64_t* hbar = rbar + 1;                                                                  // staging buffer filled
-  float* s_rstd = reinterpret_cast<float*>(hbar + 1);                                         // [GV_T]
+  float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)GV_T * xld * 2);  // [2][warp][16 lanes][4]
+  float* s_part = red + 2 * GV_RED_FLOATS;                                                  // [2][GV_T]
+  float* s_rstd = s_part + 2 * GV_T;                                                        // [GV_T]
+  int* s_gid = reinterpret_cast<int*>(s_rstd + GV_T);                                       // [stages] 2 * first unit + (two units) of the stage's row group (-1: end)
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_gid + 16);                                 // [stages] producer -> consumers
+  uint64_t* empty = full + GV_MAX_STAGES;                                                   // [stages] consumers -> producer
+  uint64_t* xbar = empty + GV_MAX_STAGES;                                                   // [n_kc] activation chunk kc has landed
+  uint64_t* rbar = xbar + GV_MAX_KC;                                                        // RMSNorm scale ready
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], GV_CWARPS);
     }
-    for (int kc = 0; kc < p.n_kc; ++kc) mbar_init(&xbar[kc], p.h32 ? GV_STHREADS : 1);
+    for (int kc = 0; kc < p.n_kc; ++kc) mbar_init(&xbar[kc], 1);
     mbar_init(rbar, 1);
-    mbar_init(hbar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmW);
   }
@@ -134,286 +130,243 @@ __global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap 
   if (p.trace && tid == 0) p.trace[blockIdx.x * 6 + 0] = gv_time();  // CTA start
 
   if (warp == GV_CWARPS) {
-    // ------------------------------ producer: one thread, up to 4 boxes of 8 KiB per stage ------------------------------
-    // Weights do not depend on the previous kernel, so the whole ring is filled before anybody waits for it.
+    // ------------------------------ producer: one thread, 4 boxes of 8 KiB per stage ------------------------------
     if (lane == 0) {
       if (!p.w_static) pdl_wait();
       const uint64_t pol = l2_policy_evict_first();
-      int st = 0, g = 0, kc = 0;
+      // work list of this CTA: its slice of the evenly split units [0, u_static), walked in row groups of gsz units (the last one
+      // may be a single unit), then row groups from the shared pool [u_static, n_units)
+      const int s1 = (int)(((long long)(blockIdx.x + 1) * p.u_static) / gridDim.x);
+      int su = (int)(((long long)blockIdx.x * p.u_static) / gridDim.x);
+      const int pool = (p.n_units - p.u_static + p.gsz - 1) / p.gsz;
+      bool waited = p.w_static == 0;
+      auto grab = [&]() {  // -> first unit of a pool group, or n_units
+        if (p.counter == nullptr) return p.n_units;
+        if (!waited) {  // the counter is shared with the previous launch, which leaves it at zero when it completes
+          pdl_wait();
+          waited = true;
+        }
+        const int v = atomicAdd(p.counter, 1);
+        if (v == pool + (int)gridDim.x - 1) *reinterpret_cast<volatile int*>(p.counter) = 0;  // the last grab of this launch
+        return v < pool ? p.u_static + v * p.gsz : p.n_units;
+      };
+      int st = 0;
       uint32_t phase = 0;
-      for (int it = 0; it < n_it; ++it) {
-        const int r_lo = gv_half_row0(p, ub, n_units, g, 0), r_hi = gv_half_row0(p, ub, n_units, g, 1);
-        const int k0 = kc * GV_SK;
-        const int n_kh = (k0 + GV_BOX_K < p.K) ? 2 : 1;   // second 512-k half absent at the end of K
-        mbar_wait(&empty[st], phase ^ 1);
-        mbar_arrive_expect_tx(&full[st], (uint32_t)(n_kh * ((r_hi >= 0) ? 2 : 1) * GV_BOX_BYTES));
-        const uint32_t dst = smem_u32(ring) + st * GV_STAGE_BYTES, bar = smem_u32(&full[st]);
-        for (int kh = 0; kh < n_kh; ++kh) {
-          tma_load_3d_hint(dst + (kh * 2) * GV_BOX_BYTES, &tmW, bar, 0, r_lo, (k0 + kh * GV_BOX_K) >> 6, pol);
-          if (r_hi >= 0) tma_load_3d_hint(dst + (kh * 2 + 1) * GV_BOX_BYTES, &tmW, bar, 0, r_hi, (k0 + kh * GV_BOX_K) >> 6, pol);
+      int u0 = su < s1 ? su : grab();
+      while (u0 < p.n_units) {
+        const int lim = u0 < p.u_static ? s1 : p.n_units;
+        const int nu = min(p.gsz, lim - u0);
+        // The group after this one is fetched while this one is being requested, so the atomic's latency hides - except
+        // for the first fetch, which has to wait for the previous kernel: then this group's stages go out first.
+        int next = -1;
+        if (u0 < p.u_static && u0 + nu < s1) next = u0 + nu;
+        else if (waited) next = grab();
+        const bool hi = p.swiglu || nu == 2;
+        const int r_lo = gv_half_row0(p, u0, 0), r_hi = gv_half_row0(p, u0, 1);
+        for (int kc = 0; kc < p.n_kc; ++kc) {
+          const int k0 = kc * GV_SK;
+          const int n_kh = (k0 + GV_BOX_K < p.K) ? 2 : 1;   // second 512-k half absent at the end of K
+          mbar_wait(&empty[st], phase ^ 1);
+          s_gid[st] = u0 * 2 + (hi ? 1 : 0);
+          mbar_arrive_expect_tx(&full[st], (uint32_t)(n_kh * (hi ? 2 : 1) * GV_BOX_BYTES));
+          const uint32_t dst = smem_u32(ring) + st * GV_STAGE_BYTES, bar = smem_u32(&full[st]);
+          for (int kh = 0; kh < n_kh; ++kh) {
+            tma_load_3d_hint(dst + (kh * 2) * GV_BOX_BYTES, &tmW, bar, 0, r_lo, (k0 + kh * GV_BOX_K) >> 6, pol);
+            if (hi) tma_load_3d_hint(dst + (kh * 2 + 1) * GV_BOX_BYTES, &tmW, bar, 0, r_hi, (k0 + kh * GV_BOX_K) >> 6, pol);
+          }
+          if (++st == p.stages) {
+            st = 0;
+            phase ^= 1;
+          }
         }
-        if (++st == p.stages) {
-          st = 0;
-          phase ^= 1;
-        }
-        if (++g == n_groups) {
-          g = 0;
-          ++kc;
-        }
+        if (next < 0) next = grab();
+        u0 = next;
       }
+      // end marker
+      mbar_wait(&empty[st], phase ^ 1);
+      s_gid[st] = -1;
+      mbar_arrive(&full[st]);
     }
     return;
   }
 
-  if (warp > GV_CWARPS) {
-    // ------------------------------ stagers: activations -> shared fp16 [GV_T][xld], one 1024-k chunk at a time ------------------------------
-    // The consumers walk K in the same order (chunk outer, row groups inner), so they start on chunk 0 while the rest is
-    // still being staged: the ~2 TB/s at which L2 serves the same activation lines to all 148 CTAs stays off the critical path.
-    const int stid = tid - GV_CTHREADS - 32;
-    if (p.h32 == nullptr) {
-      // rows >= T are never copied: zero them once
-      for (int i = stid; i < (GV_T - p.T) * (xld >> 3); i += GV_STHREADS)
-        *reinterpret_cast<uint4*>(xs + (size_t)p.T * xld + i * 8) = make_uint4(0u, 0u, 0u, 0u);
-      asm volatile("bar.sync 2, %0;" ::"n"(GV_STHREADS) : "memory");
-      if (stid == 0) {
-        fence_proxy_async_smem();
-        pdl_wait();
-        for (int kc = 0; kc < p.n_kc; ++kc) {
-          const int k0 = kc * GV_SK;
-          const uint32_t bytes = (uint32_t)min(GV_SK, p.K - k0) * 2;
-          mbar_arrive_expect_tx(&xbar[kc], bytes * p.T);
-          for (int t = 0; t < p.T; ++t)
-            bulk_g2s(smem_u32(xs + (size_t)t * xld + k0), p.x + (long long)t * p.ldx + k0, bytes, smem_u32(&xbar[kc]));
-        }
+  if (warp == GV_CWARPS + 1) {
+    // ------------------ stager: activations -> shared fp16 [GV_T][xld] by TMA, one 1024-k chunk per barrier ------------------
+    // rows >= T are never copied: zero them once
+    for (int i = lane; i < (GV_T - p.T) * (xld >> 3); i += 32)
+      *reinterpret_cast<uint4*>(xs + (size_t)p.T * xld + i * 8) = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    pdl_wait();
+    if (lane == 0) {
+      fence_proxy_async_smem();
+      for (int kc = 0; kc < p.n_kc; ++kc) {
+        const int k0 = kc * GV_SK;
+        const uint32_t bytes = (uint32_t)min(GV_SK, p.K - k0) * 2;
+        mbar_arrive_expect_tx(&xbar[kc], bytes * p.T);
+        for (int t = 0; t < p.T; ++t)
+          bulk_g2s(smem_u32(xs + (size_t)t * xld + k0), p.x + (long long)t * p.ldx + k0, bytes, smem_u32(&xbar[kc]));
       }
-      if (p.in_ss) {
-        // RMSNorm scale from the producer's per-CTA sums of squares (summed in CTA order: deterministic); needed by the
-        // epilogue only, so its latency is off the critical path
-        if (stid != 0) pdl_wait();
-        if (stid < GV_T) {
-          const int parts = (int)__ldcg(p.in_ss);
-          float tot = 0.f;
-          for (int c = 0; c < parts; ++c) tot += __ldcg(p.in_ss + 4 + c * GV_T + stid);
-          s_rstd[stid] = rsqrtf(tot / p.K + p.eps);
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(GV_STHREADS) : "memory");
-        if (stid == 0) mbar_arrive(rbar);
-      }
-    } else {
-      // LlamaRMSNorm (modeling_llama.py:66-74): x = h * rsqrt(mean(h^2) + eps) * gamma. The per-token scale is a scalar, so
-      // it is applied in the epilogue (the GEMV is linear in x) and the chunks of rn_f16(h * gamma) can be staged while the
-      // sum of squares is still being accumulated.
-      // The fp32 rows arrive by TMA bulk copy, 512 k at a time, in an 8 KiB staging buffer (LSU loads issued under the
-      // saturated weight stream take ~2.5 us per round trip on B200; the TMA path does not queue behind it).
-      float ss[GV_T] = {0.f, 0.f, 0.f, 0.f};
-      const float4* hb4 = reinterpret_cast<const float4*>(hbuf);
-      const float4* gb4 = hb4 + GV_T * (GV_HK / 4);   // gamma slice rides along in the same transfer group
-      const int n_half = (p.K + GV_HK - 1) / GV_HK;
-      pdl_wait();
-      if (p.trace && stid == 0) p.trace[blockIdx.x * 6 + 1] = gv_time();  // predecessor released
-      uint32_t hph = 0;
-      for (int hh = 0; hh < n_half; ++hh) {
-        const int k0 = hh * GV_HK;
-        const int nk = min(GV_HK, p.K - k0);
-        if (stid == 0) {
-          mbar_arrive_expect_tx(hbar, (uint32_t)((p.T + 1) * nk * 4));
-          for (int t = 0; t < p.T; ++t) bulk_g2s(smem_u32(hbuf + t * GV_HK), p.h32 + (long long)t * p.ldh + k0, (uint32_t)nk * 4, smem_u32(hbar));
-          bulk_g2s(smem_u32(hbuf + GV_T * GV_HK), p.gamma + k0, (uint32_t)nk * 4, smem_u32(hbar));
-        }
-        mbar_wait(hbar, hph);
-        hph ^= 1;
+    }
+    if (p.in_ss) {
+      // RMSNorm scale from the producer's per-item sums of squares; needed by the first item epilogue only
+      // lane l sums the items l / 4, l / 4 + 8, ... of token l % 4, then a fixed shuffle tree: deterministic
+      const int parts = (int)__ldcg(p.in_ss);
+      float tot = 0.f;
+      for (int c = lane >> 2; c < parts; c += 8) tot += __ldcg(p.in_ss + 4 + c * GV_T + (lane & 3));
 #pragma unroll
-        for (int t = 0; t < GV_T; ++t) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int c = stid + j * GV_STHREADS;
-            if (c * 4 < nk) {
-              const float4 v = t < p.T ? hb4[t * (GV_HK / 4) + c] : make_float4(0.f, 0.f, 0.f, 0.f);
-              ss[t] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-              const float4 gm = gb4[c];
-              const __half2 a = __floats2half2_rn(v.x * gm.x, v.y * gm.y);
-              const __half2 b = __floats2half2_rn(v.z * gm.z, v.w * gm.w);
-              uint2 u;
-              u.x = *reinterpret_cast<const uint32_t*>(&a);
-              u.y = *reinterpret_cast<const uint32_t*>(&b);
-              *reinterpret_cast<uint2*>(xs + (size_t)t * xld + k0 + c * 4) = u;
-            }
-          }
-        }
-        if ((hh & 1) || hh == n_half - 1) {
-          mbar_arrive(&xbar[hh >> 1]);  // both halves of the 1024-k chunk are staged (this thread's part)
-          if (p.trace && stid == 0 && hh <= 1) p.trace[blockIdx.x * 6 + 3] = gv_time();  // fused RMSNorm: first 1024-k chunk staged
-          if (p.trace && stid == 0 && hh == n_half - 1) p.trace[blockIdx.x * 6 + 4] = gv_time();  // fused RMSNorm: all chunks staged
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(GV_STHREADS) : "memory");  // staging buffer free for the next copy
-      }
-#pragma unroll
-      for (int t = 0; t < GV_T; ++t) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss[t] += __shfl_xor_sync(0xffffffffu, ss[t], o);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int t = 0; t < GV_T; ++t) s_part[(warp - GV_CWARPS - 1) * GV_T + t] = ss[t];
-      }
-      asm volatile("bar.sync 2, %0;" ::"n"(GV_STHREADS) : "memory");
-      if (stid == 0) {
-#pragma unroll
-        for (int t = 0; t < GV_T; ++t) {
-          float tot = 0.f;
-          for (int w = 0; w < GV_SWARPS; ++w) tot += s_part[w * GV_T + t];
-          s_rstd[t] = rsqrtf(tot / p.K + p.eps);
-        }
-        mbar_arrive(rbar);
-      }
+      for (int o = 4; o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane < GV_T) s_rstd[lane] = rsqrtf(tot / p.K + p.eps);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rbar);
     }
     return;
   }
 
   // ------------------------------ consumers ------------------------------
   pdl_wait();
-  if (p.trace && tid == 0 && !p.h32) p.trace[blockIdx.x * 6 + 1] = gv_time();  // predecessor released
+  if (p.trace && tid == 0) p.trace[blockIdx.x * 6 + 1] = gv_time();  // predecessor released
 
-  // ---- main loop: per iteration this warp multiplies its 16 x 128 slice of the stage with its 128 x 8 slice of x ----
   // Stage layout = 4 TMA boxes [k half][row half], each [8 k-blocks][8 rows][128 bytes] with the 128-byte swizzle (16-byte
   // unit u of row r sits at unit u ^ r): ldmatrix.x4 fetches (rows 0-7, k 0-7) (rows 8-15, k 0-7) (rows 0-7, k 8-15)
-  // (rows 8-15, k 8-15) of a 16 x 16 A fragment without bank conflicts.
+  // (rows 8-15, k 8-15) of a 16 x 16 A fragment without bank conflicts. A one-unit group leaves the high boxes stale: the
+  // fragment's upper half then holds garbage and its results are dropped.
   // B fragments (activations): b0 = x[n][k .. k+1], b1 = x[n][k+8 .. k+9] with n = lane / 4, k = 2 * (lane % 4); n >= 4 -> 0
   const int a_r = lane & 7, a_rh = (lane >> 3) & 1, a_hi = lane >> 4;
   // this warp's 128 k = k-blocks 2 * (warp % 4), + 1 of k half warp / 4
   const uint32_t a_lane = smem_u32(ring) + ((warp >> 2) * 2 + a_rh) * GV_BOX_BYTES + (warp & 3) * 2 * 1024 + a_r * 128;
-  // D fragment: lane l holds tokens 2 * (l % 4) + {0, 1}: only lanes with l % 4 < 2 carry tokens 0..3
+  // D fragment: lane l holds (row l/4, tokens 2 * (l % 4) + {0, 1}) in d[0..1] and (row l/4 + 8, same tokens) in d[2..3]:
+  // only lanes with l % 4 < 2 carry tokens 0..3
   const bool d_lane = (lane & 3) < 2;
-  float4* red_w = red + (size_t)warp * p.max_groups * 16 + (lane >> 2) * 2 + (lane & 1);
+  const int d_slot = (warp * 16 + (lane >> 2) * 2 + (lane & 1)) * 4;
   const int b_n = lane >> 2, b_k = (lane & 3) * 2;
   const __half* xb = xs + (size_t)(b_n < GV_T ? b_n : 0) * xld + warp * GV_WK + b_k;
-  int g = 0, kc = 0, st = 0;
+  // epilogue role: one (row, token) of a row group per thread for the first 64 (plain) / 32 (SwiGLU: pair, token) threads
+  const int e_t = tid & 3, e_r = tid >> 2;
+  const int e_l = (e_r & 7) * 2 + (e_t >> 1), e_j = (e_t & 1) + 2 * ((e_r >> 3) & 1);  // lane slot / component of (e_r, e_t)
+  int kc = 0, st = 0, n_done = 0;
   uint32_t phase = 0;
-  uint32_t bfrag[GV_WK / 16][2];
-  bool mine = false;
-  for (int it = 0; it < n_it; ++it) {
-    if (g == 0) {
-      // next 1024-k chunk of the activations: wait until it is staged, then keep this warp's 128 x 8 slice in registers
-      mine = kc * GV_SK + warp * GV_WK < p.K;  // K is a multiple of 128: a warp's slice is whole or absent
-      mbar_wait(&xbar[kc], 0);
-      if (p.trace && tid == 0 && it == 0) p.trace[blockIdx.x * 6 + 2] = gv_time();  // first activation chunk staged
-      if (mine) {
-#pragma unroll
-        for (int ks = 0; ks < GV_WK / 16; ++ks) {
-          bfrag[ks][0] = b_n < GV_T ? *reinterpret_cast<const uint32_t*>(xb + kc * GV_SK + ks * 16) : 0u;
-          bfrag[ks][1] = b_n < GV_T ? *reinterpret_cast<const uint32_t*>(xb + kc * GV_SK + ks * 16 + 8) : 0u;
-        }
-      }
-    }
+  float pre_res = 0.f, pre_gam = 0.f, pre_bias = 0.f;
+  bool have_scale = p.in_ss == nullptr;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  for (;;) {
     mbar_wait(&full[st], phase);
-    if (p.trace && tid == 0 && it == 0 && !p.h32) p.trace[blockIdx.x * 6 + 3] = gv_time();  // first stage landed
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
-    if (mine) {
+    const int g = s_gid[st];
+    if (g < 0) break;
+    if (p.trace && tid == 0 && n_done == 0 && kc == 0) p.trace[blockIdx.x * 6 + 3] = gv_time();  // first weight stage landed
+    if (kc == 0 && !p.swiglu && tid < 16 * GV_T) {
+      // epilogue operands of this thread's (row, token): requested now, a whole row group of streaming ahead of their use
+      // (a global load issued under the saturated weight stream takes 2-3 us)
+      const int row = (g >> 1) * 8 + e_r;
+      const bool ok = e_r < ((g & 1) ? 16 : 8) && e_t < p.T && row < p.F;
+      pre_res = 0.f;
+      pre_gam = 0.f;
+      pre_bias = 0.f;
+      if (ok && p.res) {
+        pre_res = (p.res_dtype == MYR_F32) ? __ldcg(reinterpret_cast<const float*>(p.res) + (long long)e_t * p.ldr + row)
+                                           : __half2float(__ldcg(reinterpret_cast<const __half*>(p.res) + (long long)e_t * p.ldr + row));
+      }
+      if (ok && p.post16) pre_gam = __ldg(p.post_gamma + row);
+      if (ok && p.bias) pre_bias = __half2float(__ldg(p.bias + row));
+    }
+    if (n_done == 0) {
+      mbar_wait(&xbar[kc], 0);  // the first group walks K while the later activation chunks are still landing
+      if (p.trace && tid == 0 && kc == 0) p.trace[blockIdx.x * 6 + 2] = gv_time();  // first activation chunk landed
+    }
+    if (kc * GV_SK + warp * GV_WK < p.K) {  // K is a multiple of 128: a warp's slice is whole or absent
       const uint32_t a_st = a_lane + (uint32_t)st * GV_STAGE_BYTES;
+      const __half* xk = xb + kc * GV_SK;
 #pragma unroll
       for (int ks = 0; ks < GV_WK / 16; ++ks) {
         uint32_t a[4];
         ldmatrix_x4(a_st + (ks >> 2) * 1024 + (((((ks & 3) << 1) + a_hi) ^ a_r) << 4), a);
-        mma_16816(d, a, bfrag[ks][0], bfrag[ks][1]);
+        const uint32_t b0 = b_n < GV_T ? *reinterpret_cast<const uint32_t*>(xk + ks * 16) : 0u;
+        const uint32_t b1 = b_n < GV_T ? *reinterpret_cast<const uint32_t*>(xk + ks * 16 + 8) : 0u;
+        mma_16816(d, a, b0, b1);
       }
     }
     __syncwarp();  // every lane's ldmatrix of this stage is done before the stage is handed back
     if (lane == 0) mbar_arrive(&empty[st]);
-    // running sum over the k chunks of this (warp, row group), in chunk order
-    if (d_lane) {
-      float4 acc = make_float4(d[0], d[1], d[2], d[3]);
-      if (kc > 0) {
-        const float4 o = red_w[g * 16];
-        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-      }
-      red_w[g * 16] = acc;
-    }
     if (++st == p.stages) {
       st = 0;
       phase ^= 1;
     }
-    if (++g == n_groups) {
-      g = 0;
-      ++kc;
-    }
-  }
-  if (p.h32 || p.in_ss) mbar_wait(rbar, 0);
-  consumer_sync();
-  if (p.trace && tid == 0 && !p.h32) p.trace[blockIdx.x * 6 + 4] = gv_time();  // last stage consumed
+    if (++kc < p.n_kc) continue;
 
-  // ---- cross-warp sum in warp order + epilogue ----
-  // D fragment: lane l holds (row l/4, token 2*(l%4) + {0,1}) in .x/.y and (row l/4 + 8, same tokens) in .z/.w
-  const float* redf = reinterpret_cast<const float*>(red);
-  auto total = [&](int gg, int rr, int t) {
-    const int l = (rr & 7) * 2 + (t >> 1), j = (t & 1) + 2 * (rr >> 3);
-    float a = 0.f;
-#pragma unroll
-    for (int w = 0; w < GV_CWARPS; ++w) a += redf[(((size_t)w * p.max_groups + gg) * 16 + l) * 4 + j];
-    return (p.h32 || p.in_ss) ? a * s_rstd[t] : a;  // fused RMSNorm: the per-token scale factored out of the dot product
-  };
-  if (!p.swiglu) {
-    const int row0 = ub * GV_UR, n_rows = min(n_units * GV_UR, p.F - row0);
-    float ssq = 0.f;  // this thread's token is tid % GV_T in every iteration (GV_CTHREADS is a multiple of GV_T)
-    for (int i = tid; i < n_rows * GV_T; i += GV_CTHREADS) {
-      const int u = i / GV_T, t = i % GV_T;
-      if (t >= p.T) continue;
-      const int row = row0 + u;
-      float a = total(u >> 4, u & 15, t);
-      if (p.bias) a += __half2float(p.bias[row]);
-      if (p.res) {
-        a += (p.res_dtype == MYR_F32) ? reinterpret_cast<const float*>(p.res)[(long long)t * p.ldr + row]
-                                      : __half2float(reinterpret_cast<const __half*>(p.res)[(long long)t * p.ldr + row]);
-      }
-      if (p.out_dtype == MYR_F32)
-        reinterpret_cast<float*>(p.out)[(long long)t * p.ldo + row] = a;
-      else
-        reinterpret_cast<__half*>(p.out)[(long long)t * p.ldo + row] = __float2half_rn(a);
-      if (p.post16) {
-        // hand-over to the next projection's RMSNorm: its activations without the per-token scale, and this slice's sum of squares
-        p.post16[(long long)t * p.post_ld + row] = __float2half_rn(a * p.post_gamma[row]);
-        ssq = fmaf(a, a, ssq);
-      }
+    // ---- group complete: the 8 warps' partial sums meet in shared memory (double-buffered: one barrier per group) ----
+    kc = 0;
+    float* rb = red + (n_done & 1) * GV_RED_FLOATS;
+    ++n_done;
+    if (d_lane) *reinterpret_cast<float4*>(rb + d_slot) = make_float4(d[0], d[1], d[2], d[3]);
+    d[0] = d[1] = d[2] = d[3] = 0.f;
+    if (!have_scale) {
+      mbar_wait(rbar, 0);
+      have_scale = true;
     }
-    if (p.post16) {
+    consumer_sync();
+    auto total = [&](int l, int j) {
+      float a = 0.f;
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);  // lanes with the same token
-      if (lane < GV_T) s_part[warp * GV_T + lane] = ssq;
-      consumer_sync();
-      if (tid < GV_T) {
-        float tot = 0.f;
-        for (int w = 0; w < GV_CWARPS; ++w) tot += s_part[w * GV_T + tid];
-        p.post_ss[4 + blockIdx.x * GV_T + tid] = tot;
-        if (blockIdx.x == 0 && tid == 0) p.post_ss[0] = (float)gridDim.x;
+      for (int w = 0; w < GV_CWARPS; ++w) a += rb[(w * 16 + l) * 4 + j];
+      return a;
+    };
+    const int u0 = g >> 1;
+    if (!p.swiglu) {
+      const int row = u0 * 8 + e_r;
+      float sq = 0.f;
+      if (tid < ((g & 1) ? 16 : 8) * GV_T && e_t < p.T && row < p.F) {
+        float a = total(e_l, e_j);
+        if (p.in_ss) a *= s_rstd[e_t];  // RMSNorm: the per-token scale factored out of the dot product
+        a += pre_bias;
+        a += pre_res;
+        if (p.out_dtype == MYR_F32)
+          reinterpret_cast<float*>(p.out)[(long long)e_t * p.ldo + row] = a;
+        else
+          reinterpret_cast<__half*>(p.out)[(long long)e_t * p.ldo + row] = __float2half_rn(a);
+        if (p.post16) {
+          // hand-over to the next projection's RMSNorm: its activations without the per-token scale + this CTA's sum of squares
+          p.post16[(long long)e_t * p.post_ld + row] = __float2half_rn(a * pre_gam);
+          sq = a * a;
+        }
       }
-    }
-  } else {
-    // SwiGLU (modeling_llama.py:139-140) with the rounding points of the unfused path: gate / up rounded to fp16 first
-    for (int i = tid; i < n_units * GV_UR * GV_T; i += GV_CTHREADS) {
-      const int u = i / GV_T, t = i % GV_T;
-      if (t >= p.T) continue;
-      const float a = round_f16(total(u >> 3, u & 7, t)), b = round_f16(total(u >> 3, (u & 7) + 8, t));
-      reinterpret_cast<__half*>(p.out)[(long long)t * p.ldo + ub * GV_UR + u] = __float2half_rn(silu_f(a) * b);
+      if (p.post16 && warp < 1 + (g & 1)) {
+        // sum of squares per token of each 8-row unit (warp 0: rows 0-7, warp 1: rows 8-15; lanes with the same token, fixed
+        // shuffle tree -> deterministic and independent of which CTA ran the unit)
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane < GV_T) p.post_ss[4 + (u0 + warp) * GV_T + lane] = sq;
+        if (u0 == 0 && tid == 0) p.post_ss[0] = (float)p.n_units;
+      }
+    } else if (tid < 8 * GV_T && e_t < p.T) {
+      // SwiGLU (modeling_llama.py:139-140) with the rounding points of the unfused path: gate / up rounded to fp16 first;
+      // pair e_r of the group: gate row = slot e_r, up row = slot e_r + 8 (component + 2 of the same lane slot)
+      float a = total(e_l, e_j), b = total(e_l, e_j + 2);
+      if (p.in_ss) {
+        a *= s_rstd[e_t];
+        b *= s_rstd[e_t];
+      }
+      a = round_f16(a);
+      b = round_f16(b);
+      reinterpret_cast<__half*>(p.out)[(long long)e_t * p.ldo + u0 * 8 + e_r] = __float2half_rn(silu_f(a) * b);
     }
   }
-  if (p.trace && tid == 0) p.trace[blockIdx.x * 6 + 5] = gv_time();  // epilogue done
+  if (p.trace && tid == 0) p.trace[blockIdx.x * 6 + 4] = gv_time();  // last stage consumed
+  if (p.trace && tid == 0) p.trace[blockIdx.x * 6 + 5] = gv_time();  // done
 }
 
 }  // namespace myr
 
 using namespace myr;
 
-// Called by myr_gemm_f16 for T <= 4 (see gemv_eligible in gemm.cu). Returns MYR_OK or an error code.
-int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream) {
+// Called by myr_gemm_f16 for T <= 4 (see gemv_eligible in gemm.cu). `counter`: one zero-initialised int of the caller's
+// workspace (or null). Returns MYR_OK or an error code.
+int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter) {
   GemvParams p;
   p.F = a->F; p.K = a->K; p.T = a->T;
   p.x = reinterpret_cast<const __half*>(a->x); p.ldx = a->ldx;
-  p.h32 = reinterpret_cast<const float*>(a->norm_h32); p.ldh = a->norm_ldh;
-  p.gamma = reinterpret_cast<const float*>(a->norm_gamma); p.eps = a->norm_eps;
-  p.in_ss = reinterpret_cast<const float*>(a->norm_ss);
+  p.in_ss = reinterpret_cast<const float*>(a->norm_ss); p.eps = a->norm_eps;
   p.post_gamma = reinterpret_cast<const float*>(a->post_gamma);
   p.post16 = reinterpret_cast<__half*>(a->post_out16); p.post_ld = a->post_ld;
   p.post_ss = reinterpret_cast<float*>(a->post_ss);
-  MYR_CHECK_ARG(!(p.in_ss && p.h32), "gemm: norm_h32 and norm_ss are alternatives");
   MYR_CHECK_ARG(p.post16 == nullptr || (p.post_gamma && p.post_ss && !(a->act == MYR_ACT_SWIGLU) && a->post_ld > 0),
                 "gemm: post_out16 needs post_gamma, post_ss, a row stride and a plain (non-SwiGLU) epilogue");
   p.bias = reinterpret_cast<const __half*>(a->bias);
@@ -425,55 +378,48 @@ int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream) {
   p.n_kc = ceil_div(a->K, GV_SK);
   p.kp = ceil_div(a->K, GV_WK) * GV_WK;
   MYR_CHECK_ARG(p.n_kc <= GV_MAX_KC, "gemm: K=%d exceeds the small-batch path (K <= %d)", a->K, GV_MAX_KC * GV_SK);
-  if (p.h32) {
-    MYR_CHECK_ARG(p.gamma != nullptr && a->norm_ldh % 4 == 0 && (reinterpret_cast<uintptr_t>(p.h32) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(p.gamma) & 15) == 0,
-                  "gemm: fused RMSNorm needs 16-byte aligned fp32 rows");
-  }
   // weights as a 3-D tensor: (64 k, F rows, K / 64 k-blocks); one box = 64 x 8 rows x 8 k-blocks = 8 KiB, 128-byte swizzled
   CUtensorMap tmW;
   {
     const uint64_t dims[3] = {64, (uint64_t)a->F, (uint64_t)(a->K / 64)};
     const uint64_t strides[2] = {(uint64_t)a->ldw * 2, 128};
-    const uint32_t box[3] = {64, GV_UR, GV_BOX_K / 64};
+    const uint32_t box[3] = {64, 8, GV_BOX_K / 64};
     const int rc = make_tmap_f16(&tmW, a->w, 3, dims, strides, box);
     if (rc) return rc;
   }
   const int sms = sm_count();
-  p.units = p.swiglu ? a->F / 16 : ceil_div(a->F, GV_UR);
-  const size_t x_bytes = (size_t)GV_T * (p.kp + GV_XPAD) * 2;
-  // one CTA per SM; more (several waves) only when a slice's partial sums would crowd the weight ring out of shared memory
-  for (int grid = p.units < sms ? p.units : sms;; grid *= 2) {
-    if (grid > p.units) grid = p.units;
-    const int upc = ceil_div(p.units, grid);
-    p.max_groups = p.swiglu ? upc : (upc + 1) / 2;
-    const size_t red_bytes = (size_t)GV_CWARPS * p.max_groups * 16 * sizeof(float4);
-    const size_t fixed = x_bytes + red_bytes + (p.h32 ? GV_HBUF_BYTES : 0) + GV_CWARPS * GV_T * 4 + (2 * GV_MAX_STAGES + GV_MAX_KC + 2) * 8 +
-                         GV_T * 4 + 1024;
-    // leave ~8 KB of the SM's shared memory to a small co-resident CTA of the next kernel (decode attention pre-loads its K rows
-    // while this kernel streams) unless that would cost a ring stage of an already shallow ring
-    static long long budget = -1;
-    if (budget < 0) {
-      const char* e = getenv("MYR_GEMV_SMEM_KB");
-      budget = e ? atoll(e) * 1024 : (long long)GV_SMEM_BUDGET - 8192;
-    }
-    int stages = (int)((budget - (long long)fixed) / GV_STAGE_BYTES);
-    if (stages < 4) stages = (int)(((long long)GV_SMEM_BUDGET - (long long)fixed) / GV_STAGE_BYTES);
-    if (stages > GV_MAX_STAGES) stages = GV_MAX_STAGES;
-    if (stages >= 3 || (stages >= 2 && grid == p.units)) {
-      p.stages = stages;
-      static bool attr_set = false;
-      if (!attr_set) {
-        MYR_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-      }
-      MYR_CHECK_CUDA(launch_kernel(gemv_kernel, dim3((unsigned)grid), dim3(GV_THREADS), (size_t)stages * GV_STAGE_BYTES + fixed, stream,
-                                   a->pdl != 0, tmW, p));
-      MYR_CHECK_LAUNCH();
-      return MYR_OK;
-    }
-    if (grid == p.units) break;
+  p.n_units = p.swiglu ? a->F / 16 : ceil_div(a->F, 8);
+  p.gsz = p.swiglu ? 1 : 2;
+  const int n_groups = ceil_div(p.n_units, p.gsz);
+  const int grid = n_groups < sms ? n_groups : sms;
+  static int dyn = -1;
+  if (dyn < 0) {
+    const char* e = getenv("MYR_GEMV_DYNAMIC");
+    dyn = (e && e[0] == '0') ? 0 : 1;
   }
-  set_error("gemm: K=%d does not fit the small-batch path", a->K);
-  return MYR_ERR_UNSUPPORTED;
+  // ~3/4 of the units by index (requested before the PDL wait), the rest from the counter - when a CTA has enough row groups
+  // for that to be finer than the even split (o_proj / down_proj have < 2 groups per CTA: evenly split units only)
+  p.counter = (dyn && n_groups >= 4 * grid) ? counter : nullptr;
+  p.u_static = p.counter ? (int)((long long)p.n_units * 3 / 4) / p.gsz * p.gsz : p.n_units;
+  const size_t fixed = (size_t)GV_T * (p.kp + GV_XPAD) * 2 + (2 * GV_RED_FLOATS + 3 * GV_T + 16) * 4 +
+                       (2 * GV_MAX_STAGES + GV_MAX_KC + 1) * 8 + 1024;
+  // leave ~8 KB of the SM's shared memory to a small co-resident CTA of the next kernel (decode attention pre-loads its K rows
+  // while this kernel streams) unless that would cost a ring stage of an already shallow ring
+  int stages = (int)(((long long)GV_SMEM_BUDGET - 8192 - (long long)fixed) / GV_STAGE_BYTES);
+  if (stages < 4) stages = (int)(((long long)GV_SMEM_BUDGET - (long long)fixed) / GV_STAGE_BYTES);
+  if (stages > GV_MAX_STAGES) stages = GV_MAX_STAGES;
+  if (stages < 2) {
+    set_error("gemm: K=%d does not fit the small-batch path", a->K);
+    return MYR_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MYR_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  MYR_CHECK_CUDA(launch_kernel(gemv_kernel, dim3((unsigned)grid), dim3(GV_THREADS), (size_t)stages * GV_STAGE_BYTES + fixed, stream,
+                               a->pdl != 0, tmW, p));
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
 }

@@ -35,8 +35,8 @@ class _Obj:
 
 
 def l_hidden_ok(dims):
-    """The fused RMSNorm prologue of csrc/gemv.cu holds one fp32 row slice per thread: hidden <= 4096, multiple of 8."""
-    return dims.llama.hidden <= 4096 and dims.llama.hidden % 8 == 0
+    """The small-batch kernel of csrc/gemv.cu (and its RMSNorm hand-over) needs K % 128 == 0 for every LLaMA projection."""
+    return dims.llama.hidden % 128 == 0 and dims.llama.inter % 128 == 0
 
 
 class MyriadEngine:
@@ -346,16 +346,14 @@ class MyriadEngine:
         x16, qkv, ctx, _, act = bufs
         kc, vc = self.kcache[li], self.vcache[li]
         ldq = qkv.shape[1]
-        # T <= 4 (greedy decode at the reference's batch sizes): the small-batch weight-streaming kernel computes the RMSNorm
-        # in its own prologue, so a layer is 5 dependent launches instead of 7
+        # T <= 4 (greedy decode at the reference's batch sizes): the small-batch weight-streaming kernels hand the RMSNorm over
+        # between themselves, so a layer is 5 dependent launches instead of 7
         fuse = T <= 4 and self.fuse_small_batch_norm
         # decode steps also hand the RMSNorm over between launches: o_proj / down_proj write rn_f16(h * gamma_next) and their
         # slice's sum of squares next to the fp32 stream, the next projection copies those rows and only applies the scale
         hand = hand if fuse else None
         if hand is not None and li > 0:
             K.gemm(hand.yb, L.wqkv, out=qkv, w_static=True, norm_ss=(hand.ssb, l.eps))
-        elif fuse:
-            K.gemm(None, L.wqkv, out=qkv, w_static=True, norm=(h32, L.n1, l.eps))
         else:
             K.norm(h32, L.n1, None, l.eps, rms=True, out16=x16)
             K.gemm(x16, L.wqkv, out=qkv, w_static=True)
@@ -377,11 +375,8 @@ class MyriadEngine:
             K.gemm(act, L.wd, res=h32, out=h32, w_static=True, post_norm=(next_gamma, hand.yb, hand.ssb))
             return
         K.gemm(ctx, L.wo, res=h32, out=h32, w_static=True)
-        if fuse:
-            K.gemm(None, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm=(h32, L.n2, l.eps))
-        else:
-            K.norm(h32, L.n2, None, l.eps, rms=True, out16=x16)
-            K.gemm(x16, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
+        K.norm(h32, L.n2, None, l.eps, rms=True, out16=x16)
+        K.gemm(x16, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
         K.gemm(act, L.wd, res=h32, out=h32, w_static=True)
 
     def _llama_bufs(self, T):
@@ -425,8 +420,6 @@ class MyriadEngine:
             self._llama_layer(L, li, st.h32, st.bufs, B, 1, st.pos, st.kv_len, 0, st.cache_off, st.Skv, False, hand=hand, next_gamma=nxt)
         if hand is not None:
             K.gemm(hand.yb, self.llw.lm_head, out=st.logits, w_static=True, norm_ss=(hand.ssb, l.eps))
-        elif B <= 4 and self.fuse_small_batch_norm:
-            K.gemm(None, self.llw.lm_head, out=st.logits, w_static=True, norm=(st.h32, self.llw.norm, l.eps))
         else:
             K.norm(st.h32, self.llw.norm, None, l.eps, rms=True, out16=st.bufs[0])
             K.gemm(st.bufs[0], self.llw.lm_head, out=st.logits, w_static=True)

@@ -52,14 +52,17 @@ for gemv in (True, False):
     tot = sum(w[0].numel() * 2 for w in (wq, wo, wgu, wd)) / 1e6
     print("%s layer chain (4 GEMMs, %.0f MB): %.2f us/layer  %.2f TB/s" % (name, tot, t, tot / t), flush=True)
     if gemv:
+        ya, yb = torch.zeros(T, 4096, device=dev, dtype=torch.float16), torch.zeros(T, 4096, device=dev, dtype=torch.float16)
+        ssa, ssb = torch.zeros(K.NORM_SS_FLOATS, device=dev), torch.zeros(K.NORM_SS_FLOATS, device=dev)
+        ssb[0] = 1.0
         def layer_chain_norm():
             for i in range(NL):
-                K.gemm(None, wq[i], out=qkv, w_static=True, norm=(h, gamma, 1e-6))
-                K.gemm(x, wo[i], res=h, out=h, w_static=True)
-                K.gemm(None, wgu[i], act=K.ACT_SWIGLU, out=act, w_static=True, norm=(h, gamma, 1e-6))
-                K.gemm(a, wd[i], res=h, out=h, w_static=True)
+                K.gemm(yb, wq[i], out=qkv, w_static=True, norm_ss=(ssb, 1e-6))
+                K.gemm(x, wo[i], res=h, out=h, w_static=True, post_norm=(gamma, ya, ssa))
+                K.gemm(ya, wgu[i], act=K.ACT_SWIGLU, out=act, w_static=True, norm_ss=(ssa, 1e-6))
+                K.gemm(a, wd[i], res=h, out=h, w_static=True, post_norm=(gamma, yb, ssb))
         t = timeit(layer_chain_norm) / NL
-        print("%s layer chain with fused RMSNorm prologues: %.2f us/layer  %.2f TB/s" % (name, t, tot / t), flush=True)
+        print("%s layer chain with the RMSNorm hand-over: %.2f us/layer  %.2f TB/s" % (name, t, tot / t), flush=True)
 K.set_gemv(True)
 # steady state: one long launch (F = 65536, K = 4096: 537 MB) and (F = 16384, K = 11008: 361 MB)
 for F, Kd in ((65536, 4096), (16384, 11008)):

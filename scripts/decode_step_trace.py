@@ -13,7 +13,7 @@ torch.manual_seed(0)
 x = (torch.randn(4, 131, 4096, device=dev) * 0.5)
 eng.greedy_decode(x.clone(), 8, ((100000,),))
 st = list(eng._decode_graphs.values())[0]
-n_k = 5 * dims.llama.layers + 1
+n_k = 5 * dims.llama.layers + 2
 buf = torch.zeros(n_k * 148 * 6, dtype=torch.int64, device=dev)
 K.lib().myr_gemm_set_trace(ctypes.c_void_p(buf.data_ptr()))
 g = torch.cuda.CUDAGraph()

@@ -27,10 +27,13 @@ for i in range(2):
     wgu = (torch.randn(22016, 4096, device=dev) * 0.02).half()
     wd = (torch.randn(4096, 11008, device=dev) * 0.02).half()
     gamma = torch.ones(4096, device=dev)
-    K.gemm(None, wq, out=qkv, w_static=True, norm=(res, gamma, 1e-6))  # small-batch kernel (gemv.cu), fused RMSNorm prologue
-    K.gemm(x, wo, res=res, out=res, w_static=True)
-    K.gemm(None, wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm=(res, gamma, 1e-6))
-    K.gemm(a, wd, res=res, out=res, w_static=True)
+    ya, yb = torch.zeros(B, 4096, device=dev, dtype=torch.float16), torch.zeros(B, 4096, device=dev, dtype=torch.float16)
+    ssa, ssb = torch.zeros(K.NORM_SS_FLOATS, device=dev), torch.zeros(K.NORM_SS_FLOATS, device=dev)
+    K.gemm(a, wd, res=res, out=res, w_static=True, post_norm=(gamma, yb, ssb))  # small-batch kernel (gemv.cu), RMSNorm hand-over
+    K.gemm(yb, wq, out=qkv, w_static=True, norm_ss=(ssb, 1e-6))
+    K.gemm(x, wo, res=res, out=res, w_static=True, post_norm=(gamma, ya, ssa))
+    K.gemm(ya, wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm_ss=(ssa, 1e-6))
+    K.gemm(a, wd, res=res, out=res, w_static=True, post_norm=(gamma, yb, ssb))
 # ViT GEMMs at the bench batch (T = 4 * 257): qkv, fc1 + GELU, fc2 + residual
 T = B * 257
 h = torch.randn(T, 1408, device=dev).half()

@@ -1,5 +1,5 @@
 """GPU: the small-batch (T <= 4) weight-streaming kernel (csrc/gemv.cu) behind myr_gemm_f16 against the fp32 definition,
-against the tcgen05 kernel it stands in for, and — for the fused RMSNorm prologue — against the oracle's LlamaRMSNorm
+against the tcgen05 kernel it stands in for, and — for the RMSNorm hand-over — against the oracle's LlamaRMSNorm
 (modeling_llama.py:66-74). Tolerance: fp16 operands, fp32 accumulation -> 1e-3 of the output scale; outputs of repeated
 launches must be bit-identical (fixed-order reductions)."""
 import pytest
@@ -104,28 +104,13 @@ def test_gemv_swiglu(K, T, I, Kd):
     assert (y != y_tc).float().mean().item() < 0.05  # one fp16 ulp where the fp32 sums round differently
 
 
-@pytest.mark.parametrize("T,D,F", [(4, 4096, 12304), (1, 4096, 32000), (3, 256, 520), (4, 1408, 64)])
-def test_gemv_fused_rmsnorm_prologue(K, O, T, D, F):
-    """x = LlamaRMSNorm(h) computed inside the kernel == norm kernel + GEMM, == oracle norm followed by an fp32 matmul."""
-    h = rnd(T, D, seed=5, std=2.0)
-    gamma = 1.0 + 0.1 * rnd(D, seed=6)
-    w = (rnd(F, D, seed=7) / D ** 0.5).half()
-    hd, gd, wd = h.to(dev()), gamma.to(dev()), w.to(dev())
-    y = K.gemm(None, wd, norm=(hd, gd, 1e-6), out=torch.empty(T, F, device=dev(), dtype=torch.float32), w_static=True)
-    x16 = torch.empty(T, D, device=dev(), dtype=torch.float16)
-    K.norm(hd, gd, None, 1e-6, rms=True, out16=x16)
-    y2 = K.gemm(x16, wd, out_dtype=torch.float32)
-    close(y, y2, 5e-4, "fused norm vs norm kernel + gemv")
-    xn = O.rms_norm(h, gamma, 1e-6)
-    close(y, xn @ w.float().t(), 2e-3, "fused norm vs oracle")
-
-
-def test_fused_norm_rejected_on_large_batch(K):
-    """The prologue exists on the T <= 4 path only; the tensor-core path must refuse it loudly, not ignore it."""
-    h = rnd(8, 256, seed=1).to(dev())
+def test_hand_over_rejected_on_large_batch(K):
+    """The RMSNorm hand-over exists on the T <= 4 path only; the tensor-core path must refuse it loudly, not ignore it."""
+    x = rnd(8, 256, seed=1).half().to(dev())
     w = rnd(64, 256, seed=2).half().to(dev())
+    ss = torch.zeros(K.NORM_SS_FLOATS, device=dev())
     with pytest.raises(RuntimeError):
-        K.gemm(None, w, norm=(h, torch.ones(256, device=dev()), 1e-6), out=torch.empty(8, 64, device=dev(), dtype=torch.float16))
+        K.gemm(x, w, norm_ss=(ss, 1e-6))
 
 
 def test_gemv_dependent_chain_in_cuda_graph(K):
@@ -143,9 +128,12 @@ def test_gemv_dependent_chain_in_cuda_graph(K):
     h = h0.clone()
     act = torch.empty(T, I, device=dev(), dtype=torch.float16)
 
+    y16 = torch.zeros(T, D, device=dev(), dtype=torch.float16)
+    ss = torch.zeros(K.NORM_SS_FLOATS, device=dev(), dtype=torch.float32)
+
     def chain():
-        K.gemm(ctx, wo, res=h, out=h, w_static=True)
-        K.gemm(None, wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm=(h, gamma, 1e-6))
+        K.gemm(ctx, wo, res=h, out=h, w_static=True, post_norm=(gamma, y16, ss))
+        K.gemm(y16, wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm_ss=(ss, 1e-6))
         K.gemm(act, wd, res=h, out=h, w_static=True)
 
     chain()
@@ -154,7 +142,7 @@ def test_gemv_dependent_chain_in_cuda_graph(K):
     # fp32 definition with the kernels' rounding points
     r = h0.cpu() + ctx.float().cpu() @ wo.float().cpu().t()
     xn = (r * torch.rsqrt(r.pow(2).mean(-1, keepdim=True) + 1e-6) * gamma.cpu()).half().float()
-    a = (torch.nn.functional.silu((xn @ g.float().t()).half().float()) * (xn @ u.float().t()).half().float()).half().float()
+    a = (torch.nn.functional.silu((xn @ g.float().t()).half().float()) * (xn @ u.float().t()).half().float()).half().float()  # noqa
     ref = r + a @ wd.float().cpu().t()
     close(eager, ref, 2e-3, "chain vs fp32 definition")
     graph = torch.cuda.CUDAGraph()
@@ -192,5 +180,7 @@ def test_gemv_rmsnorm_hand_over(K, O):
     tot = ss[4:4 + 4 * int(ss[0].item())].reshape(-1, 4).sum(0).cpu()
     close(tot, href.pow(2).sum(-1), 1e-4, "sum of squares partials")
     close(y, O.rms_norm(href, gamma.cpu(), 1e-6) @ w.float().cpu().t(), 2e-3, "hand-over vs oracle")
-    y2 = K.gemm(None, w, norm=(h, gamma, 1e-6), out=torch.empty(T, F, device=dev(), dtype=torch.float32), w_static=True)
-    close(y, y2, 5e-4, "hand-over vs in-kernel norm")
+    x16 = torch.empty(T, D, device=dev(), dtype=torch.float16)
+    K.norm(h, gamma, None, 1e-6, rms=True, out16=x16)
+    y2 = K.gemm(x16, w, out_dtype=torch.float32, w_static=True)
+    close(y, y2, 5e-4, "hand-over vs norm kernel + projection")
