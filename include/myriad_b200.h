@@ -181,6 +181,8 @@ typedef struct {
   void* out; int64_t ldo;                /* fp16 [B, H * dh] */
   int64_t next_layer_stride;             /* elements between this layer's and the next layer's cache (0 = last layer): the
                                             kernel prefetches the next layer's slice into L2 */
+  int32_t kv_cap;                        /* 0, or an upper bound (<= 256, <= cache_len) on kv_len for this launch (and every replay
+                                            of a graph holding it): K / V then arrive by TMA in 512 * kv_cap bytes of shared memory */
 } myr_decode_attn_args;
 int myr_decode_attention(const myr_decode_attn_args* args, void* stream);
 

@@ -199,6 +199,180 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
   stamp(5);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared-memory variant (caches of up to 256 visible tokens): the (head, sequence) slice of K and V arrives by TMA - two
+// 128-byte-swizzled boxes of [kv_cap rows][64 halfs] each - instead of per-thread global loads. On B200 a global load issued
+// while a weight-streaming kernel saturates the memory system takes 2-3 us per round trip, and the register version needs
+// two to three dependent ones after the qkv projection (second K batch, V batches); TMA transfers do not queue behind the
+// stream and are requested BEFORE the programmatic-dependent-launch wait (every cached row was written at least one decode
+// step ago). After the wait the kernel only reads the new token's q / k / v (+ LoRA rows), everything else is in shared
+// memory. Arithmetic and reduction order are those of decode_attn_task. The CTA needs 512 bytes per cache row, so it does
+// not share an SM with a full-ring weight-streaming CTA: it starts as the qkv projection's CTA on its SM exits, and the
+// o_proj CTA follows it (measured on B200: 2.47 ms per decode step against 2.57 ms with the register version co-resident
+// with both; a shallower o_proj ring that would fit next to it costs more than it gains).
+struct DecodeAttnTmaParams {
+  DecodeAttnParams a;
+  int kv_cap;  // rows per box (multiple of 8, <= 256)
+};
+
+__global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __grid_constant__ CUtensorMap tmK,
+                                                                      const __grid_constant__ CUtensorMap tmV,
+                                                                      const DecodeAttnTmaParams pp) {
+  const DecodeAttnParams& p = pp.a;
+  extern __shared__ uint8_t da_smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(da_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tile_bytes = pp.kv_cap * 128;  // one [kv_cap][64 halfs] box
+  uint8_t* sK = tiles;                     // [2 dh halves][kv_cap][128 B], 16-byte unit u of row r at unit u ^ (r & 7)
+  uint8_t* sV = tiles + 2 * tile_bytes;
+  float* s_scores = reinterpret_cast<float*>(tiles + 4 * tile_bytes);  // [kv_cap]
+  __shared__ DecodeAttnSmem sm;
+  __shared__ uint64_t bar;
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int HD = p.H * DA_DH;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  long long* tr = (p.trace && tid == 0) ? p.trace + (blockIdx.y * gridDim.x + blockIdx.x) * 6 : nullptr;
+  auto stamp = [&](int i) {
+    if (tr) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      tr[i] = t;
+    }
+  };
+  stamp(0);
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar, (uint32_t)(4 * tile_bytes));
+    for (int hf = 0; hf < 2; ++hf) {
+      tma_load_4d(sK + hf * tile_bytes, &tmK, &bar, hf * 64, h, 0, b);
+      tma_load_4d(sV + hf * tile_bytes, &tmV, &bar, hf * 64, h, 0, b);
+    }
+  }
+  // step state is written by the greedy-update kernel at the END of the previous decode step: safe ahead of the wait
+  const int off = p.cache_off ? __ldcg(p.cache_off) : p.cache_off_host;
+  int kvl = p.kv_len ? __ldcg(p.kv_len + b) : off + 1;
+  if (kvl > pp.kv_cap) kvl = pp.kv_cap;
+  __half* kbase = p.kcache + (size_t)b * p.c_bs + h * DA_DH;
+  __half* vbase = p.vcache + (size_t)b * p.c_bs + h * DA_DH;
+  const int pos = __ldcg(p.pos + b);
+  const int jr = tid & (DA_DH / 2 - 1);
+  const float c = p.cos_t[(size_t)pos * (DA_DH / 2) + jr], sn = p.sin_t[(size_t)pos * (DA_DH / 2) + jr];
+  pdl_wait();
+  stamp(1);
+
+  // ---- phase 0: q / k / v of the new token: LoRA, rotation, cache append (one rotary pair per thread)
+  const __half* row = p.qkv + (size_t)b * p.ldq;
+  if (tid < DA_DH / 2) {
+    const int j = tid, half = DA_DH / 2;
+    float q1 = __half2float(__ldcg(row + h * DA_DH + j)), q2 = __half2float(__ldcg(row + h * DA_DH + half + j));
+    const float k1 = __half2float(__ldcg(row + HD + h * DA_DH + j)), k2 = __half2float(__ldcg(row + HD + h * DA_DH + half + j));
+    float v1 = __half2float(__ldcg(row + 2 * HD + h * DA_DH + j)), v2 = __half2float(__ldcg(row + 2 * HD + h * DA_DH + half + j));
+    if (p.lora_r) {
+      float xq[8], xv[8];
+      da_unpack8(__ldcg(reinterpret_cast<const uint4*>(row + 3 * HD)), xq);
+      da_unpack8(__ldcg(reinterpret_cast<const uint4*>(row + 3 * HD + 8)), xv);
+      q1 = fmaf(p.lora_scale, da_lora_dot(p.lora_bq, h * DA_DH + j, xq), q1);
+      q2 = fmaf(p.lora_scale, da_lora_dot(p.lora_bq, h * DA_DH + half + j, xq), q2);
+      v1 = fmaf(p.lora_scale, da_lora_dot(p.lora_bv, h * DA_DH + j, xv), v1);
+      v2 = fmaf(p.lora_scale, da_lora_dot(p.lora_bv, h * DA_DH + half + j, xv), v2);
+    }
+    // fp16 rounding of the rotated q / k and of v: the values the prefill path stores (q in place, k / v in the cache)
+    sm.q[j] = round_f16(q1 * c - q2 * sn);
+    sm.q[half + j] = round_f16(q2 * c + q1 * sn);
+    const __half ko1 = __float2half_rn(k1 * c - k2 * sn), ko2 = __float2half_rn(k2 * c + k1 * sn);
+    const __half vo1 = __float2half_rn(v1), vo2 = __float2half_rn(v2);
+    sm.k[j] = ko1; sm.k[half + j] = ko2;
+    sm.v[j] = vo1; sm.v[half + j] = vo2;
+    if (off >= 0 && off < p.Smax) {
+      __half* kd = kbase + (size_t)off * p.c_ts;
+      __half* vd = vbase + (size_t)off * p.c_ts;
+      kd[j] = ko1; kd[half + j] = ko2;
+      vd[j] = vo1; vd[half + j] = vo2;
+    }
+  }
+  mbar_wait(&bar, 0);  // K / V tiles have landed (requested before the wait)
+  __syncthreads();
+  stamp(2);
+
+  // ---- phase 1: scores, one key per thread and pass; rows come from the swizzled tiles (the new token's from sm.k)
+  for (int j = tid; j < kvl; j += DA_THREADS) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < DA_DH / 8; ++i) {
+      const uint4 raw = (j == off) ? reinterpret_cast<const uint4*>(sm.k)[i]
+                                   : *reinterpret_cast<const uint4*>(sK + (i >> 3) * tile_bytes + j * 128 + (((i & 7) ^ (j & 7)) << 4));
+      float kf[8];
+      da_unpack8(raw, kf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(kf[e], sm.q[i * 8 + e], d);
+    }
+    s_scores[j] = d * p.scale;
+  }
+  __syncthreads();
+  stamp(3);
+
+  // ---- softmax statistics (fp32)
+  float m = -INFINITY;
+  for (int j = tid; j < kvl; j += DA_THREADS) m = fmaxf(m, s_scores[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) sm.red[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(sm.red[0], sm.red[1]), fmaxf(sm.red[2], sm.red[3]));
+  __syncthreads();
+  float l = 0.f;
+  for (int j = tid; j < kvl; j += DA_THREADS) {
+    const float e = __expf(s_scores[j] - m);
+    s_scores[j] = e;
+    l += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if (lane == 0) sm.red[warp] = l;
+  __syncthreads();
+  l = (sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]);
+  stamp(4);
+
+  // ---- phase 2: O = P V. Warp w owns keys j = w (mod 4) in increasing order; lane l owns dims [4l, 4l + 4)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int v_half = lane >> 4, v_unit = (lane & 15) >> 1, v_sub = (lane & 1) * 8;
+  for (int j = warp; j < kvl; j += 4) {
+    const float pj = s_scores[j];
+    const uint2 raw = (j == off) ? *reinterpret_cast<const uint2*>(sm.v + lane * 4)
+                                 : *reinterpret_cast<const uint2*>(sV + v_half * tile_bytes + j * 128 + ((v_unit ^ (j & 7)) << 4) + v_sub);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+    const float2 a = __half22float2(h2[0]), bb = __half22float2(h2[1]);
+    acc[0] = fmaf(pj, a.x, acc[0]);
+    acc[1] = fmaf(pj, a.y, acc[1]);
+    acc[2] = fmaf(pj, bb.x, acc[2]);
+    acc[3] = fmaf(pj, bb.y, acc[3]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sm.acc[warp][lane * 4 + i] = acc[i];
+  if (p.next_layer_stride) {
+    // ask L2 for the next layer's slice of the cache now (its attention runs ~80 us from now; weights are loaded
+    // evict-first, so the lines survive until then)
+    const __half* kn = kbase + p.next_layer_stride;
+    const __half* vn = vbase + p.next_layer_stride;
+    for (int j = tid; j < 2 * kvl; j += DA_THREADS) {  // one 128-byte line = half a K or V row
+      const size_t o = (size_t)(j >> 1) * p.c_ts + (j & 1) * 64;
+      prefetch_l2(kn + o);
+      prefetch_l2(vn + o);
+    }
+  }
+  __syncthreads();
+  {
+    const float o = (sm.acc[0][tid] + sm.acc[1][tid]) + (sm.acc[2][tid] + sm.acc[3][tid]);
+    p.out[(size_t)b * p.ldo + h * DA_DH + tid] = __float2half_rn(l > 0.f ? o / l : 0.f);
+  }
+  stamp(5);
+}
+
 }  // namespace myr
 
 using namespace myr;
@@ -227,7 +401,36 @@ extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_
   p.scale = a->scale;
   p.out = reinterpret_cast<__half*>(a->out); p.ldo = a->ldo;
   p.next_layer_stride = a->next_layer_stride;
-  p.trace = (a->B * a->H <= 148) ? next_trace_slot() : nullptr;
+  p.trace = nullptr;
+  // shared-memory variant: the caller bounds the visible cache (kv_cap <= 256 rows) for the lifetime of the launch / graph
+  if (a->kv_cap > 0 && a->kv_cap <= 256 && a->kv_cap <= a->cache_len) {
+    DecodeAttnTmaParams pp;
+    pp.a = p;
+    pp.a.trace = (a->B * a->H <= 148) ? next_trace_slot() : nullptr;
+    pp.kv_cap = (a->kv_cap + 7) / 8 * 8;
+    CUtensorMap tmK, tmV;
+    {
+      const void* ptrs[2] = {a->kcache, a->vcache};
+      CUtensorMap* maps[2] = {&tmK, &tmV};
+      for (int i = 0; i < 2; ++i) {
+        const uint64_t dims[4] = {(uint64_t)DA_DH, (uint64_t)a->H, (uint64_t)a->cache_len, (uint64_t)a->B};
+        const uint64_t strides[3] = {(uint64_t)DA_DH * 2, (uint64_t)a->cache_token_stride * 2, (uint64_t)a->cache_batch_stride * 2};
+        const uint32_t box[4] = {64, 1, (uint32_t)pp.kv_cap, 1};
+        const int rc = make_tmap_f16(maps[i], ptrs[i], 4, dims, strides, box);
+        if (rc) return rc;
+      }
+    }
+    const size_t smem = (size_t)pp.kv_cap * (4 * 128 + 4) + 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      MYR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      MYR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      attr2 = true;
+    }
+    MYR_CHECK_CUDA(launch_kernel(decode_attn_tma_kernel, dim3(a->H, a->B), dim3(DA_THREADS), smem, stream, true, tmK, tmV, pp));
+    MYR_CHECK_LAUNCH();
+    return MYR_OK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     // same L1 / shared-memory split as the weight-streaming kernels around it: an SM only hosts CTAs of two kernels at once
@@ -235,6 +438,7 @@ extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_
     MYR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
+  p.trace = (a->B * a->H <= 148) ? next_trace_slot() : nullptr;
   MYR_CHECK_CUDA(launch_kernel(decode_attn_kernel, dim3(a->H, a->B), dim3(DA_THREADS), (size_t)a->cache_len * sizeof(float), stream,
                                true, p));
   MYR_CHECK_LAUNCH();

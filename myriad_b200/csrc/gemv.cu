@@ -416,6 +416,9 @@ int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter)
   static bool attr_set = false;
   if (!attr_set) {
     MYR_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // always the largest shared-memory carve-out, also for launches with a shallow ring: an SM hosts CTAs of two kernels at
+    // once only under one carve-out, and switching it waits for the SM to drain
+    MYR_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   MYR_CHECK_CUDA(launch_kernel(gemv_kernel, dim3((unsigned)grid), dim3(GV_THREADS), (size_t)stages * GV_STAGE_BYTES + fixed, stream,

@@ -13,6 +13,7 @@ residual streams / softmax / norm statistics. The reference's CUDA path keeps fp
 Q-Former (autocast) — keeping them in fp32 only moves results closer to the fp32 CPU oracle.
 """
 import math
+import os
 
 import torch
 
@@ -337,7 +338,8 @@ class MyriadEngine:
             self.vcache = torch.zeros_like(self.kcache)
             self._decode_graphs = {}
 
-    def _llama_layer(self, L, li, h32, bufs, B, S, pos, kv_len, cache_off, cache_off_dev, Skv, causal, hand=None, next_gamma=None):
+    def _llama_layer(self, L, li, h32, bufs, B, S, pos, kv_len, cache_off, cache_off_dev, Skv, causal, hand=None, next_gamma=None,
+                     kv_cap=0):
         """LlamaDecoderLayer.forward modeling_llama.py:247-299 as 8 launches: RMSNorm -> qkv (+ LoRA A rows) GEMM -> RoPE +
         LoRA B + KV-cache append -> flash attention -> o_proj GEMM (+ residual) -> RMSNorm -> gate/up GEMM with fused
         SwiGLU -> down GEMM (+ residual). Weights are static, so each GEMM may prefetch them under the previous kernel."""
@@ -362,7 +364,7 @@ class MyriadEngine:
             # decode: rotary + LoRA-B + cache append + attention over the cache in one CUDA-core launch
             nxt = self.kcache.stride(0) if li + 1 < l.layers else 0
             K.decode_attention(qkv, B, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, kv_len, ctx, 1.0 / math.sqrt(dh),
-                               cache_off=cache_off, cache_off_dev=cache_off_dev, lora=lora, next_layer_stride=nxt)
+                               cache_off=cache_off, cache_off_dev=cache_off_dev, lora=lora, next_layer_stride=nxt, kv_cap=kv_cap)
         else:
             K.rope_cache(qkv, B, S, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, cache_off=cache_off,
                          cache_off_dev=cache_off_dev, lora=lora)
@@ -417,7 +419,8 @@ class MyriadEngine:
         hand = st.hand if (B <= 4 and self.fuse_small_batch_norm) else None
         for li, L in enumerate(self.llw.layers):
             nxt = self.llw.layers[li + 1].n1 if li + 1 < l.layers else self.llw.norm
-            self._llama_layer(L, li, st.h32, st.bufs, B, 1, st.pos, st.kv_len, 0, st.cache_off, st.Skv, False, hand=hand, next_gamma=nxt)
+            self._llama_layer(L, li, st.h32, st.bufs, B, 1, st.pos, st.kv_len, 0, st.cache_off, st.Skv, False, hand=hand, next_gamma=nxt,
+                              kv_cap=st.kv_cap if hand is not None else 0)
         if hand is not None:
             K.gemm(hand.yb, self.llw.lm_head, out=st.logits, w_static=True, norm_ss=(hand.ssb, l.eps))
         else:
@@ -458,10 +461,11 @@ class MyriadEngine:
         K.greedy_step(st.logits, st.state, st.scratch, st.B, l.vocab, st.max_new, st.min_new, l.eos, st.stops, st.n_stops,
                       st.stop_len)
 
-    def _decode_state(self, B, max_new, min_new, stop_seqs, Skv):
+    def _decode_state(self, B, max_new, min_new, stop_seqs, Skv, kv_cap=0):
         l, dev = self.d.llama, self.dev
         st = _Obj()
         st.B, st.max_new, st.min_new, st.Skv = B, max_new, min_new, Skv
+        st.kv_cap = kv_cap  # upper bound on the visible cache over this state's decode steps (0: unbounded)
         st.state = torch.zeros(4 + 4 * B + B * max_new, device=dev, dtype=torch.int32)
         st.unfinished = st.state[4:4 + B]
         st.cur_tok = st.state[4 + B:4 + 2 * B]
@@ -495,10 +499,12 @@ class MyriadEngine:
         B, S, _ = embeds32.shape
         self._ensure_cache(B, S + max_new_tokens)
         Skv = self.kcache.shape[2]
-        key = (B, max_new_tokens, min_new_tokens, tuple(map(tuple, stop_seqs)), Skv)
+        # decode attention keeps K / V of caches up to 256 tokens in shared memory; the bound is baked into the captured graph
+        kv_cap = S + max_new_tokens if (S + max_new_tokens <= 256 and os.environ.get("MYR_ATTN_TMA", "1") != "0") else 0
+        key = (B, max_new_tokens, min_new_tokens, tuple(map(tuple, stop_seqs)), Skv, kv_cap)
         st = self._decode_graphs.get(key)
         if st is None:
-            st = self._decode_state(B, max_new_tokens, min_new_tokens, stop_seqs, Skv)
+            st = self._decode_state(B, max_new_tokens, min_new_tokens, stop_seqs, Skv, kv_cap)
             self._decode_graphs[key] = st
         init = torch.zeros(4 + 4 * B, dtype=torch.int32)
         init[2] = S - 1

@@ -244,11 +244,12 @@ class DecodeAttnArgs(ctypes.Structure):
         ("scale", ctypes.c_float),
         ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64),
         ("next_layer_stride", ctypes.c_int64),
+        ("kv_cap", ctypes.c_int32),
     ]
 
 
 def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, scale, cache_off=0, cache_off_dev=None, lora=None,
-                     next_layer_stride=0):
+                     next_layer_stride=0, kv_cap=0):
     """One new token per sequence: LoRA-B + RoPE + KV-cache append + attention over the cache in one launch."""
     a = DecodeAttnArgs()
     a.qkv, a.ldq = qkv.data_ptr(), qkv.stride(0)
@@ -266,6 +267,7 @@ def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, 
     a.scale = scale
     a.out, a.ldo = out.data_ptr(), out.stride(0)
     a.next_layer_stride = next_layer_stride
+    a.kv_cap = kv_cap
     check(lib().myr_decode_attention(ctypes.byref(a), _stream()), "myr_decode_attention")
     return out
 

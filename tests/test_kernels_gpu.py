@@ -359,8 +359,9 @@ def test_greedy_step(K):
     assert s[4 + 2 * B:4 + 3 * B].tolist() == [13] * B and s[4 + 3 * B:4 + 4 * B].tolist() == [12] * B and int(s[2]) == 12
 
 
+@pytest.mark.parametrize("kv_cap", [0, 64, 96])  # 0: K / V through registers; else by TMA into shared memory
 @pytest.mark.parametrize("lora", [False, True])
-def test_decode_attention_matches_rope_plus_flash(K, O, lora):
+def test_decode_attention_matches_rope_plus_flash(K, O, lora, kv_cap):
     """myr_decode_attention (one launch per decode step and layer) against the prefill pair myr_rope_cache + myr_attention_fwd
     on the same cache, and against the oracle's rotary / attention arithmetic."""
     torch.manual_seed(4)
@@ -390,7 +391,7 @@ def test_decode_attention_matches_rope_plus_flash(K, O, lora):
     kc2, vc2 = kc.to(dev()).clone(), vc.to(dev()).clone()
     out = torch.empty(B, D, device=dev(), dtype=torch.float16)
     K.decode_attention(qkv.to(dev()), B, H, dh, pos.to(dev()), cosd, sind, kc2, vc2, kv_len.to(dev()), out, 1.0 / math.sqrt(dh),
-                       cache_off=off, lora=lo)
+                       cache_off=off, lora=lo, kv_cap=kv_cap)
     close(kc2, kc1, 1e-3, "appended k")
     close(vc2, vc1, 1e-3, "appended v")
     print("cache append: %d k / %d v values differ in the last bit from myr_rope_cache" % (
