@@ -262,6 +262,14 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
   const int pos = __ldcg(p.pos + b);
   const int jr = tid & (DA_DH / 2 - 1);
   const float c = p.cos_t[(size_t)pos * (DA_DH / 2) + jr], sn = p.sin_t[(size_t)pos * (DA_DH / 2) + jr];
+  // LoRA-B rows of this thread's rotary pair (static weights): in registers before the wait
+  uint4 lb[4] = {};
+  if (p.lora_r && tid < DA_DH / 2) {
+    lb[0] = __ldg(reinterpret_cast<const uint4*>(p.lora_bq + (size_t)(h * DA_DH + tid) * 8));
+    lb[1] = __ldg(reinterpret_cast<const uint4*>(p.lora_bq + (size_t)(h * DA_DH + DA_DH / 2 + tid) * 8));
+    lb[2] = __ldg(reinterpret_cast<const uint4*>(p.lora_bv + (size_t)(h * DA_DH + tid) * 8));
+    lb[3] = __ldg(reinterpret_cast<const uint4*>(p.lora_bv + (size_t)(h * DA_DH + DA_DH / 2 + tid) * 8));
+  }
   pdl_wait();
   stamp(1);
 
@@ -276,10 +284,18 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
       float xq[8], xv[8];
       da_unpack8(__ldcg(reinterpret_cast<const uint4*>(row + 3 * HD)), xq);
       da_unpack8(__ldcg(reinterpret_cast<const uint4*>(row + 3 * HD + 8)), xv);
-      q1 = fmaf(p.lora_scale, da_lora_dot(p.lora_bq, h * DA_DH + j, xq), q1);
-      q2 = fmaf(p.lora_scale, da_lora_dot(p.lora_bq, h * DA_DH + half + j, xq), q2);
-      v1 = fmaf(p.lora_scale, da_lora_dot(p.lora_bv, h * DA_DH + j, xv), v1);
-      v2 = fmaf(p.lora_scale, da_lora_dot(p.lora_bv, h * DA_DH + half + j, xv), v2);
+      auto dot8 = [](const uint4& wrow, const float (&xa)[8]) {  // same order of operations as da_lora_dot
+        float w[8];
+        da_unpack8(wrow, w);
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc = fmaf(w[r], xa[r], acc);
+        return acc;
+      };
+      q1 = fmaf(p.lora_scale, dot8(lb[0], xq), q1);
+      q2 = fmaf(p.lora_scale, dot8(lb[1], xq), q2);
+      v1 = fmaf(p.lora_scale, dot8(lb[2], xv), v1);
+      v2 = fmaf(p.lora_scale, dot8(lb[3], xv), v2);
     }
     // fp16 rounding of the rotated q / k and of v: the values the prefill path stores (q in place, k / v in the cache)
     sm.q[j] = round_f16(q1 * c - q2 * sn);
