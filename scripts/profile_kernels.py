@@ -70,5 +70,7 @@ od = torch.empty(B, Dl, device=dev, dtype=torch.float16)
 bq = torch.randn(Dl, 8, device=dev).half()
 for i in range(2):
     K.decode_attention(qd, B, 32, 128, pos, cos, cos, kc, vc, kvl, od, 1 / math.sqrt(128), cache_off=160, lora=(bq, bq, 8, 2.0))
+    # the decode step's variant: K / V tiles by TMA into shared memory (visible cache bounded by 168 rows)
+    K.decode_attention(qd, B, 32, 128, pos, cos, cos, kc, vc, kvl, od, 1 / math.sqrt(128), cache_off=160, lora=(bq, bq, 8, 2.0), kv_cap=168)
 torch.cuda.synchronize()
 print("done")
