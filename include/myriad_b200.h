@@ -38,6 +38,9 @@ enum myr_act { MYR_ACT_NONE = 0, MYR_ACT_GELU_ERF = 1, MYR_ACT_RELU = 2, MYR_ACT
 
 /* ---- library ------------------------------------------------------------------------------------- */
 int myr_version(void);                            /* ABI version (integer, bumps on breaking change) */
+/* sizeof() of an argument struct as compiled into the library (0 myr_gemm_args, 1 myr_attn_args, 2 myr_norm_args,
+ * 3 myr_rope_args, 4 myr_decode_attn_args, 5 myr_mega_op; else 0): lets a binding verify its own struct layout. */
+size_t myr_abi_sizeof(int32_t which);
 int myr_last_error(char* buf, size_t buf_bytes);  /* copies last error message of calling thread */
 int myr_device_sm_count(void);
 unsigned long long myr_launch_count(void);        /* kernels launched (or captured into a CUDA graph) by this library */

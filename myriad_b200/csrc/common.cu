@@ -97,6 +97,19 @@ extern "C" {
 
 int myr_version(void) { return 1; }
 
+/* sizeof() of the argument structs as this library was compiled: bindings check their own layout against it */
+size_t myr_abi_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(myr_gemm_args);
+    case 1: return sizeof(myr_attn_args);
+    case 2: return sizeof(myr_norm_args);
+    case 3: return sizeof(myr_rope_args);
+    case 4: return sizeof(myr_decode_attn_args);
+    case 5: return sizeof(myr_mega_op);
+    default: return 0;
+  }
+}
+
 int myr_last_error(char* buf, size_t n) {
   if (!buf || n == 0) return MYR_ERR_INVALID;
   strncpy(buf, myr::g_err, n - 1);

@@ -23,6 +23,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.myr_version() >= 1
 
 
+def test_ctypes_struct_layouts_match_the_library():
+    """The ctypes mirrors in myriad_b200/kernels.py have the size the C compiler gave the structs of include/myriad_b200.h
+    (a drifted binding would pass garbage to the kernels without any error)."""
+    from myriad_b200 import kernels as K
+    from myriad_b200._lib import lib
+    lib().myr_abi_sizeof.restype = ctypes.c_size_t
+    for which, cls in enumerate((K.GemmArgs, K.AttnArgs, K.NormArgs, K.RopeArgs, K.DecodeAttnArgs, K.MegaOp)):
+        assert lib().myr_abi_sizeof(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib().myr_abi_sizeof(99) == 0
+
+
 def test_argument_validation_needs_no_gpu():
     """Bad arguments are rejected with a status code and a message before any CUDA call (errors never throw)."""
     from myriad_b200 import kernels as K
