@@ -99,6 +99,11 @@ typedef struct {
  * one CTA: no split tiles; the last int of the workspace's counter area hands out row groups, zero on entry and on exit). myr_set_gemv(0) (or env MYR_GEMV=0) routes those shapes to the tcgen05 kernel instead;
  * returns the previous setting. */
 int32_t myr_set_gemv(int32_t enabled);
+/* Work split of a small-batch launch on a device with `sms` SMs (pure host arithmetic, no GPU needed): out8 = { units of 8
+ * output rows (SwiGLU: 8 gate/up pairs), units per 16-row MMA group, CTAs, units [0, u_static) split evenly by CTA index
+ * (the rest handed out in groups through the atomic counter), counter used (0/1), ring stages, 1024-k stages per group,
+ * bytes of shared memory besides the ring }. */
+int myr_gemv_plan(int32_t F, int32_t K, int32_t act, int32_t sms, int32_t have_counter, int32_t* out8);
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);
 int myr_gemm_f16(const myr_gemm_args* args, void* stream);
 /* Profiling aid: while set, every GEMM launch writes 148 x 6 %globaltimer stamps (CTA start, predecessor released, last MMA

@@ -357,6 +357,47 @@ __global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap 
 
 using namespace myr;
 
+// Work split and ring depth of one launch (pure host arithmetic; also exported as myr_gemv_plan for the CPU tests).
+struct GemvPlan {
+  int n_units, gsz, grid, u_static, use_counter, stages, n_kc, kp;
+  size_t fixed_smem;
+};
+static GemvPlan gemv_plan(int F, int K, bool swiglu, int sms, bool have_counter) {
+  GemvPlan pl;
+  pl.n_kc = ceil_div(K, GV_SK);
+  pl.kp = ceil_div(K, GV_WK) * GV_WK;
+  pl.n_units = swiglu ? F / 16 : ceil_div(F, 8);
+  pl.gsz = swiglu ? 1 : 2;
+  const int n_groups = ceil_div(pl.n_units, pl.gsz);
+  pl.grid = n_groups < sms ? n_groups : sms;
+  static int dyn = -1;
+  if (dyn < 0) {
+    const char* e = getenv("MYR_GEMV_DYNAMIC");
+    dyn = (e && e[0] == '0') ? 0 : 1;
+  }
+  // ~3/4 of the units by index (requested before the PDL wait), the rest from the counter - when a CTA has enough row groups
+  // for that to be finer than the even split (o_proj / down_proj have < 2 groups per CTA: evenly split units only)
+  pl.use_counter = (dyn && have_counter && n_groups >= 4 * pl.grid) ? 1 : 0;
+  pl.u_static = pl.use_counter ? (int)((long long)pl.n_units * 3 / 4) / pl.gsz * pl.gsz : pl.n_units;
+  pl.fixed_smem = (size_t)GV_T * (pl.kp + GV_XPAD) * 2 + (2 * GV_RED_FLOATS + 3 * GV_T + 16) * 4 +
+                  (2 * GV_MAX_STAGES + GV_MAX_KC + 1) * 8 + 1024;
+  // leave ~8 KB of the SM's shared memory to a small co-resident CTA of the next kernel unless that would cost a ring stage
+  // of an already shallow ring
+  int stages = (int)(((long long)GV_SMEM_BUDGET - 8192 - (long long)pl.fixed_smem) / GV_STAGE_BYTES);
+  if (stages < 4) stages = (int)(((long long)GV_SMEM_BUDGET - (long long)pl.fixed_smem) / GV_STAGE_BYTES);
+  if (stages > GV_MAX_STAGES) stages = GV_MAX_STAGES;
+  pl.stages = stages;
+  return pl;
+}
+
+extern "C" int myr_gemv_plan(int32_t F, int32_t K, int32_t act, int32_t sms, int32_t have_counter, int32_t* out8) {
+  MYR_CHECK_ARG(out8 != nullptr && F > 0 && K > 0 && K % 128 == 0 && sms > 0, "gemv_plan: bad arguments");
+  const GemvPlan pl = gemv_plan(F, K, act == MYR_ACT_SWIGLU, sms, have_counter != 0);
+  out8[0] = pl.n_units; out8[1] = pl.gsz; out8[2] = pl.grid; out8[3] = pl.u_static;
+  out8[4] = pl.use_counter; out8[5] = pl.stages; out8[6] = pl.n_kc; out8[7] = (int32_t)pl.fixed_smem;
+  return MYR_OK;
+}
+
 // Called by myr_gemm_f16 for T <= 4 (see gemv_eligible in gemm.cu). `counter`: one zero-initialised int of the caller's
 // workspace (or null). Returns MYR_OK or an error code.
 int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter) {
@@ -375,8 +416,9 @@ int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter)
   p.swiglu = a->act == MYR_ACT_SWIGLU;
   p.w_static = a->w_static;
   p.trace = next_trace_slot();
-  p.n_kc = ceil_div(a->K, GV_SK);
-  p.kp = ceil_div(a->K, GV_WK) * GV_WK;
+  const GemvPlan pl = gemv_plan(a->F, a->K, p.swiglu != 0, sm_count(), counter != nullptr);
+  p.n_kc = pl.n_kc;
+  p.kp = pl.kp;
   MYR_CHECK_ARG(p.n_kc <= GV_MAX_KC, "gemm: K=%d exceeds the small-batch path (K <= %d)", a->K, GV_MAX_KC * GV_SK);
   // weights as a 3-D tensor: (64 k, F rows, K / 64 k-blocks); one box = 64 x 8 rows x 8 k-blocks = 8 KiB, 128-byte swizzled
   CUtensorMap tmW;
@@ -387,27 +429,13 @@ int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter)
     const int rc = make_tmap_f16(&tmW, a->w, 3, dims, strides, box);
     if (rc) return rc;
   }
-  const int sms = sm_count();
-  p.n_units = p.swiglu ? a->F / 16 : ceil_div(a->F, 8);
-  p.gsz = p.swiglu ? 1 : 2;
-  const int n_groups = ceil_div(p.n_units, p.gsz);
-  const int grid = n_groups < sms ? n_groups : sms;
-  static int dyn = -1;
-  if (dyn < 0) {
-    const char* e = getenv("MYR_GEMV_DYNAMIC");
-    dyn = (e && e[0] == '0') ? 0 : 1;
-  }
-  // ~3/4 of the units by index (requested before the PDL wait), the rest from the counter - when a CTA has enough row groups
-  // for that to be finer than the even split (o_proj / down_proj have < 2 groups per CTA: evenly split units only)
-  p.counter = (dyn && n_groups >= 4 * grid) ? counter : nullptr;
-  p.u_static = p.counter ? (int)((long long)p.n_units * 3 / 4) / p.gsz * p.gsz : p.n_units;
-  const size_t fixed = (size_t)GV_T * (p.kp + GV_XPAD) * 2 + (2 * GV_RED_FLOATS + 3 * GV_T + 16) * 4 +
-                       (2 * GV_MAX_STAGES + GV_MAX_KC + 1) * 8 + 1024;
-  // leave ~8 KB of the SM's shared memory to a small co-resident CTA of the next kernel (decode attention pre-loads its K rows
-  // while this kernel streams) unless that would cost a ring stage of an already shallow ring
-  int stages = (int)(((long long)GV_SMEM_BUDGET - 8192 - (long long)fixed) / GV_STAGE_BYTES);
-  if (stages < 4) stages = (int)(((long long)GV_SMEM_BUDGET - (long long)fixed) / GV_STAGE_BYTES);
-  if (stages > GV_MAX_STAGES) stages = GV_MAX_STAGES;
+  p.n_units = pl.n_units;
+  p.gsz = pl.gsz;
+  p.counter = pl.use_counter ? counter : nullptr;
+  p.u_static = pl.u_static;
+  const int grid = pl.grid;
+  const size_t fixed = pl.fixed_smem;
+  const int stages = pl.stages;
   if (stages < 2) {
     set_error("gemm: K=%d does not fit the small-batch path", a->K);
     return MYR_ERR_UNSUPPORTED;

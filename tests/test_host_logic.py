@@ -93,3 +93,49 @@ def test_synthetic_weight_spec_matches_reference_sizes():
     assert n("llama_model.model.layers.") == 6_476_267_520 and n("llama_model.base_model") == 4_194_304  # 6.476 B + 4.19 M LoRA
     assert n("Qformer.") + n("query_tokens") == 105_162_240  # trimmed Q-Former: 105.1 M (SURVEY §8c'')
     assert spec["visual_encoder.blocks.0.mlp.fc1.weight"] == (6144, 1408) and d.vit.head_dim == 88 and d.vit.tokens == 257
+
+
+# ------------------------------------------------------------------------------------------------ small-batch kernel work split
+@pytest.mark.parametrize("F,K,act", [(4096, 4096, 0), (12304, 4096, 0), (4096, 11008, 0), (22016, 4096, 3), (32000, 4096, 0),
+                                     (5, 128, 0), (100, 128, 0), (128, 256, 3), (40000, 512, 0), (1408, 6144, 0)])
+@pytest.mark.parametrize("have_counter", [0, 1])
+def test_gemv_work_split_covers_every_unit_once(F, K, act, have_counter):
+    """csrc/gemv.cu: units of 8 output rows are either split evenly by CTA index or handed out in groups through the atomic
+    counter. Re-walk the producer's work list on the host from the plan the library computes (myr_gemv_plan, no GPU): every
+    unit is requested exactly once, groups never exceed the MMA tile, and the ring fits the shared-memory budget."""
+    import ctypes
+
+    from myriad_b200._lib import lib
+    out = (ctypes.c_int32 * 8)()
+    assert lib().myr_gemv_plan(F, K, act, 148, have_counter, out) == 0
+    n_units, gsz, grid, u_static, use_counter, stages, n_kc, fixed = list(out)
+    swiglu = act == 3
+    assert n_units == (F // 16 if swiglu else -(-F // 8)) and gsz == (1 if swiglu else 2)
+    assert 1 <= grid <= 148 and 0 <= u_static <= n_units and (not use_counter or u_static % gsz == 0)
+    assert use_counter in (0, 1) and (use_counter or u_static == n_units) and (have_counter or not use_counter)
+    assert n_kc == -(-K // 1024) and 2 <= stages <= 6 and stages * 32768 + fixed <= 227 * 1024
+    seen = [0] * n_units
+    pool = -(-(n_units - u_static) // gsz)
+    grabs = 0
+    for cta in range(grid):
+        u, s1 = cta * u_static // grid, (cta + 1) * u_static // grid
+        while u < s1:  # the CTA's slice, in row groups of gsz units; the last one may be a single unit
+            nu = min(gsz, s1 - u)
+            for i in range(nu):
+                seen[u + i] += 1
+            u += nu
+    for v in range(pool):  # groups handed out by the counter, whoever grabs them
+        u0 = u_static + v * gsz
+        nu = min(gsz, n_units - u0)
+        assert nu >= 1
+        for i in range(nu):
+            seen[u0 + i] += 1
+        grabs += 1
+    assert seen == [1] * n_units
+    if use_counter:
+        # every CTA ends on exactly one failing grab, the last of them (value pool + grid - 1) puts the counter back to zero
+        assert pool > 0 and grabs + grid == pool + grid
+    if (F, K) in ((12304, 4096), (22016, 4096), (32000, 4096)) and have_counter:
+        assert use_counter == 1 and n_units - u_static >= n_units // 4  # the large decode projections use the pool
+    if (F, K) in ((4096, 4096), (4096, 11008)):
+        assert use_counter == 0  # o_proj / down_proj: fewer than two row groups per CTA, even split only
