@@ -323,7 +323,31 @@ def roofline_probe(eng, dims, dev, peaks):
     torch.cuda.synchronize()
     ms2 = e0.elapsed_time(e1) / len(blk)
     tf = 2.0 * T * D * Hd / (ms2 / 1e3) / 1e12
-    extra = {"roofline_tensor": {"kernel": "gemm_tc_kernel (ViT fc1+GELU, T=%d F=%d K=%d)" % (T, Hd, D), "bound": "tensor",
+    # attention context (north_star: tensor-pipe share of the attention kernels): the ViT flash-attention launch at the bench batch
+    v = dims.vit
+    qkv_a = torch.randn(T, 3 * D, device=dev).half()
+    ctx_a = torch.empty(T, D, device=dev, dtype=torch.float16)
+    sa = (3 * D, v.tokens * 3 * D, v.head_dim)
+
+    def attn_once():
+        K.attention(qkv_a, qkv_a[:, D:], qkv_a[:, 2 * D:], ctx_a, B, v.heads, v.tokens, v.tokens, v.head_dim, 1.0, sa, sa, sa,
+                    (D, v.tokens * D, v.head_dim))
+
+    for _ in range(3):
+        attn_once()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        attn_once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms3 = e0.elapsed_time(e1) / 20
+    tf_a = 4.0 * B * v.heads * v.tokens * v.tokens * v.head_dim / (ms3 / 1e3) / 1e12
+    extra_attn = {"kernel": "attn_fwd_kernel (ViT, B=%d H=%d N=%d dh=%d)" % (B, v.heads, v.tokens, v.head_dim), "bound": "tensor",
+                  "achieved": tf_a, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": tf_a / peaks["tensor"], "avg_launch_us": ms3 * 1e3,
+                  "note": "latency-bound at this size (1.5 GFLOP per launch, 1 % of the step); tensor pipe 7 % active in profiles/"}
+    extra = {"roofline_attention": extra_attn,
+             "roofline_tensor": {"kernel": "gemm_tc_kernel (ViT fc1+GELU, T=%d F=%d K=%d)" % (T, Hd, D), "bound": "tensor",
                                  "achieved": tf, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": tf / peaks["tensor"],
                                  "avg_launch_us": ms2 * 1e3}}
     return roof, extra
