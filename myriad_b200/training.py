@@ -319,7 +319,18 @@ class MyriadTrainer(MyriadEngine):
             dy = torch.empty(B, Hc, Hc, cout, device=dev, dtype=F16)
             K.pool_relu_bwd(y, dx, dy, B, Hc, Hc, cout)
             rows = B * Hc * Hc
-            if cols is None:
+            if cols is None and j > 0 and (9 * cin) % 8 == 0 and cout % 8 == 0:
+                # 16 -> 64 channels at 56 x 56: the direct weight-gradient kernel needs 5.7 ms here (profiles/r1_train_phases.md);
+                # as a [64 x 12544] x [12544 x 144] tensor-core GEMM over the im2col matrix it is tens of microseconds
+                c2 = torch.empty(rows, 9 * cin, device=dev, dtype=F16)
+                K.im2col(x, c2, B, Hc, Hc, cin, 3, 3, 1)
+                dy2 = dy.reshape(rows, cout)
+                K.gemm(dy2, c2, out=gw.reshape(cout, 9 * cin), x_mn_major=True, w_mn_major=True, T=cout, F=9 * cin, K=rows, bn_hint=64,
+                       alpha=inv_scale)
+                K.colsum(dy2, cout, 0, 1, rows, cout, gb, scale=inv_scale)
+                dx = torch.empty(B, Hc, Hc, cin, device=dev, dtype=F16)
+                K.conv3x3_dgrad(dy, W.direct[j][0], dx, B, Hc, Hc, cin, cout)
+            elif cols is None:
                 K.conv3x3_wgrad(x, dy, gw, gb, B, Hc, Hc, cin, cout, inv_scale)
                 if j > 0:
                     dx = torch.empty(B, Hc, Hc, cin, device=dev, dtype=F16)

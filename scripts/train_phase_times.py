@@ -28,6 +28,13 @@ for name, label in (("vit_forward", "vit fwd"), ("build_inputs_embeds", "encode 
                     ("_llama_train_fwd", "llama fwd (+ lm_head)"), ("_llama_train_bwd", "llama bwd"), ("_qformer_bwd", "q-former bwd"),
                     ("optimizer_step", "all-reduce + AdamW + refresh")):
     wrap(tr, name, label)
+FINE = (("_ve_head_bwd", "expert head bwd (1x1 / 5x5 conv wgrad + trunk bwd)"), ("_conv_trunk_bwd", "  conv trunk bwd"),
+        ("_conv_trunk_train", "  conv trunk fwd (inside encode fwd)"))
+for name, label in FINE:
+    wrap(tr, name, label)
+import myriad_b200.training as T_
+for name, label in (("clamp_ce_fwd", "clamp-CE fwd"), ("clamp_ce_bwd", "clamp-CE bwd"), ("adaptor_bwd", "adaptor bwd"), ("memset_zero", "zero flat grads")):
+    wrap(T_.K, name, label)
 for _ in range(3):
     tr.train_step(image, maps, 1, ids_b, ids_a, text, tmask)
 torch.cuda.synchronize()
@@ -43,3 +50,9 @@ for rep in range(2):
     for label in ("vit fwd", "encode fwd (vit + adaptor + q-former + experts + embeds)", "llama fwd (+ lm_head)", "llama bwd", "q-former bwd",
                   "all-reduce + AdamW + refresh"):
         print("  %-62s %.2f ms" % (label, d[label + ":begin"].elapsed_time(d[label + ":end"])))
+    # phases that run several times per step: summed over their calls
+    for label in [l for _, l in FINE] + ["clamp-CE fwd", "clamp-CE bwd", "adaptor bwd", "zero flat grads"]:
+        b = [e for n, e in marks if n == label + ":begin"]
+        e_ = [e for n, e in marks if n == label + ":end"]
+        if b:
+            print("  %-62s %.2f ms (%d calls)" % (label, sum(x.elapsed_time(y) for x, y in zip(b, e_)), len(b)))
