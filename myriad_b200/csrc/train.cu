@@ -313,6 +313,34 @@ __global__ void colsum_kernel(const void* __restrict__ src, int src_dtype, long 
   }
 }
 
+// Same sums with the rows spread over a block (opt-in with MYR_COLSUM_BLOCK=1 until it has been through the GPU parity tests:
+// written at the end of round 1 when no GPU slot was left to run them). One block per 32 columns, 32 warps: warp w adds the rows
+// w, w + 32, ... (coalesced 32-column reads), the 32 partial sums per column meet in shared memory and are added in warp order:
+// deterministic, and a bias gradient over 12 544 rows is ~400 dependent adds per thread instead of 12 544.
+__global__ void __launch_bounds__(1024) colsum_block_kernel(const void* __restrict__ src, int src_dtype, long long ld, long long gs, int groups,
+                                                      int rows, int D, float scale, float* __restrict__ out, int accumulate) {
+  __shared__ float part[32][33];
+  const int cx = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float a = 0.f;
+  if (c < D) {
+    const long long total = (long long)groups * rows;
+    for (long long i = wy; i < total; i += 32) {
+      const long long g = i / rows, r = i - g * rows;
+      const long long o = g * gs + r * ld + c;
+      a += src_dtype == MYR_F32 ? reinterpret_cast<const float*>(src)[o] : __half2float(reinterpret_cast<const __half*>(src)[o]);
+    }
+  }
+  part[wy][cx] = a;
+  __syncthreads();
+  if (wy == 0 && c < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) t += part[w][cx];
+    out[c] = (accumulate ? out[c] : 0.f) + scale * t;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // LoraAdaptorV2 backward (networks.py:81-93, y = x + W2 (W1 x)): weights only (x comes from the frozen ViT).
 //   pass 1 (one warp per row): t = W1 x, dt = W2^T dy          -> td [rows, 2 * rank]
@@ -504,8 +532,17 @@ extern "C" int myr_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_
                           int32_t D, float scale, void* out, int32_t accumulate, void* stream_) {
   STREAM;
   MYR_CHECK_ARG(src && out && groups > 0 && rows > 0 && D > 0, "colsum: bad arguments");
-  colsum_kernel<<<ceil_div(D, 128), 128, 0, stream>>>(src, src_dtype, ld, group_stride, groups, rows, D, scale,
-                                                     reinterpret_cast<float*>(out), accumulate);
+  static int block_variant = -1;
+  if (block_variant < 0) {
+    const char* e = getenv("MYR_COLSUM_BLOCK");
+    block_variant = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (block_variant)
+    colsum_block_kernel<<<ceil_div(D, 32), 1024, 0, stream>>>(src, src_dtype, ld, group_stride, groups, rows, D, scale,
+                                                             reinterpret_cast<float*>(out), accumulate);
+  else
+    colsum_kernel<<<ceil_div(D, 128), 128, 0, stream>>>(src, src_dtype, ld, group_stride, groups, rows, D, scale,
+                                                       reinterpret_cast<float*>(out), accumulate);
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }
