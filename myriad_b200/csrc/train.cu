@@ -313,8 +313,8 @@ __global__ void colsum_kernel(const void* __restrict__ src, int src_dtype, long 
   }
 }
 
-// Same sums with the rows spread over a block (opt-in with MYR_COLSUM_BLOCK=1 until it has been through the GPU parity tests:
-// written at the end of round 1 when no GPU slot was left to run them). One block per 32 columns, 32 warps: warp w adds the rows
+// Same sums with the rows spread over a block (the default; MYR_COLSUM_BLOCK=0 selects the one-thread-per-column kernel
+// above). One block per 32 columns, 32 warps: warp w adds the rows
 // w, w + 32, ... (coalesced 32-column reads), the 32 partial sums per column meet in shared memory and are added in warp order:
 // deterministic, and a bias gradient over 12 544 rows is ~400 dependent adds per thread instead of 12 544.
 __global__ void __launch_bounds__(1024) colsum_block_kernel(const void* __restrict__ src, int src_dtype, long long ld, long long gs, int groups,
@@ -535,7 +535,7 @@ extern "C" int myr_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_
   static int block_variant = -1;
   if (block_variant < 0) {
     const char* e = getenv("MYR_COLSUM_BLOCK");
-    block_variant = (e && e[0] == '1') ? 1 : 0;
+    block_variant = (e && e[0] == '0') ? 0 : 1;
   }
   if (block_variant)
     colsum_block_kernel<<<ceil_div(D, 32), 1024, 0, stream>>>(src, src_dtype, ld, group_stride, groups, rows, D, scale,
