@@ -306,7 +306,11 @@ def roofline_probe(eng, dims, dev, peaks):
     achieved = (wbytes + abytes) / (ms / 1e3) / 1e9
     kname = "gemv_kernel" if fused else "gemm_tc_kernel"
     roof = {"kernel": "%s (decode, T=%d: norm+qkv+loraA / o+res / norm+gate_up+swiglu / down+res of all 32 layers)" % (kname, B), "bound": "hbm",
-            "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
+            "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four launches of a layer, from the committed
+            # `ncu --set full` capture of these launches (profiles/r1_ncu_full_pass3.md rows 0-3: 90.38 + 3.66, 100.87 + 3.67,
+            # 33.70 + 0.00, 180.43 + 3.41 MB); not re-measured by this run
+            "traffic": 104.03e6 if fused else None,
             "peak_source": peaks["src"], "avg_launch_us": ms * 1e3 / n_launch, "algorithmic_bytes_per_launch": per_launch}
     # tensor-bound context: the ViT MLP GEMMs at the bench batch (T = B * 257)
     T, D, Hd = B * dims.vit.tokens, dims.vit.dim, dims.vit.mlp_hidden
