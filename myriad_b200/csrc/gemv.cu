@@ -51,7 +51,7 @@ constexpr int GV_RED_FLOATS = GV_CWARPS * 16 * 4; // one work item's D fragments
 struct GemvParams {
   int F, K, T;
   const __half* x; long long ldx;                 // fp16 activations [T, K]
-  const float* in_ss; float eps;                  // optional: x lacks the RMSNorm scale; per-CTA sums of squares of its producer
+  const float* in_ss; float eps;                  // optional: x lacks the RMSNorm scale; per-unit sums of squares written by its producer
   const float* post_gamma; __half* post16; long long post_ld; float* post_ss;  // producer side of that hand-over
   const __half* bias;
   const void* res; int res_dtype; long long ldr;
@@ -107,7 +107,7 @@ __global__ void __maxnreg__(96) gemv_kernel(const __grid_constant__ CUtensorMap 
   uint8_t* ring = smem;
   __half* xs = reinterpret_cast<__half*>(ring + (size_t)p.stages * GV_STAGE_BYTES);       // [GV_T][xld]
   float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + (size_t)GV_T * xld * 2);  // [2][warp][16 lanes][4]
-  float* s_part = red + 2 * GV_RED_FLOATS;                                                  // [2][GV_T]
+  float* s_part = red + 2 * GV_RED_FLOATS;                                                  // [2][GV_T] (spare)
   float* s_rstd = s_part + 2 * GV_T;                                                        // [GV_T]
   int* s_gid = reinterpret_cast<int*>(s_rstd + GV_T);                                       // [stages] 2 * first unit + (two units) of the stage's row group (-1: end)
   uint64_t* full = reinterpret_cast<uint64_t*>(s_gid + 16);                                 // [stages] producer -> consumers

@@ -76,7 +76,7 @@ def gemm(x, w, bias=None, act=ACT_NONE, res=None, out=None, out_dtype=torch.floa
     # batch = (nb0, nb1, (x_bs0, x_bs1), (w_bs0, w_bs1), (o_bs0, o_bs1)): independent problems, element strides
     """out[t, f] = epilogue(sum_k x[t, k] * w[f, k]);  x: [T, K] fp16 (row stride may exceed K), w: [F, K] fp16.
     post_norm = (gamma [F] fp32, y16 [T, F] fp16, ss [NORM_SS_FLOATS] fp32): producer side of an RMSNorm hand-over (T <= 4): also
-    writes y16 = rn_f16(out * gamma) and per-CTA sums of out^2; the consumer passes x = y16, norm_ss = (ss, eps)."""
+    writes y16 = rn_f16(out * gamma) and the sums of out^2 over each block of 8 features; the consumer passes x = y16, norm_ss = (ss, eps)."""
     assert x.dtype == torch.float16 and w.dtype == torch.float16
     assert x.stride(-1) == 1 and w.stride(-1) == 1
     assert batch is None or (T is not None and F is not None and K is not None and out is not None and ldo is not None)
