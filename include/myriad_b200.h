@@ -4,7 +4,7 @@
  * The reference (tzjtatata/Myriad) is 100 % Python and has NO FFI/plugin ABI: its only
  * plug-in point is the Python class registry (minigpt4/common/registry.py:83-109). This header is therefore
  * the *new* boundary: one extern "C" entry point per fused device op that the registry-registered replacement
- * modules (minigpt4/models/*.py in this repo) call through ctypes. Every entry point cites the reference
+ * modules (the minigpt4/models package in this repo) call through ctypes. Every entry point cites the reference
  * code whose eager ATen kernels it replaces.
  *
  * Conventions

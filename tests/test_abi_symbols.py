@@ -23,6 +23,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.myr_version() >= 1
 
 
+def test_header_is_plain_c():
+    """include/myriad_b200.h is the boundary a non-C++ host binds to: it must compile as C99 on its own."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    r = subprocess.run([gcc, "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", os.path.join(ROOT, "include", "myriad_b200.h")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+
+
 def test_ctypes_struct_layouts_match_the_library():
     """The ctypes mirrors in myriad_b200/kernels.py have the size the C compiler gave the structs of include/myriad_b200.h
     (a drifted binding would pass garbage to the kernels without any error)."""
