@@ -362,18 +362,29 @@ def test_greedy_step(K):
 @pytest.mark.parametrize("kv_cap", [0, 64, 96])  # 0: K / V through registers; else by TMA into shared memory
 @pytest.mark.parametrize("lora", [False, True])
 def test_decode_attention_matches_rope_plus_flash(K, O, lora, kv_cap):
+    _decode_attention_case(K, O, lora, kv_cap, B=3, H=4, Smax=96, past=[40, 57, 1], off=60)
+
+
+@pytest.mark.parametrize("off", [131, 147, 162])
+@pytest.mark.parametrize("kv_cap", [0, 163])
+def test_decode_attention_bench_shape(K, O, kv_cap, off):
+    """The decode-attention launch of the benchmark itself (bench.py / BASELINE configs[2]): 32 heads, 4 sequences, cache of
+    131 prefill + up to 32 new tokens => kv_cap = 163 (engine.py greedy_decode), visible cache 132 ... 163."""
+    _decode_attention_case(K, O, True, kv_cap, B=4, H=32, Smax=163, past=[off, off, off - 7, 3], off=off)
+
+
+def _decode_attention_case(K, O, lora, kv_cap, B, H, Smax, past, off):
     """myr_decode_attention (one launch per decode step and layer) against the prefill pair myr_rope_cache + myr_attention_fwd
     on the same cache, and against the oracle's rotary / attention arithmetic."""
     torch.manual_seed(4)
-    B, H, dh, Smax, r = 3, 4, 128, 96, 8
+    dh, r = 128, 8
     D = H * dh
     ldq = 3 * D + (2 * r if lora else 0)
-    past = [40, 57, 1]
     kc = (torch.randn(B, Smax, D) * 0.5).half()
     vc = (torch.randn(B, Smax, D) * 0.5).half()
     qkv = (torch.randn(B, ldq) * 0.5).half()
     bq, bv = (torch.randn(D, r) * 0.05).half(), (torch.randn(D, r) * 0.05).half()
-    off = 60  # the graph-replayed decode writes every row's new token to the same slot; rows are right-aligned by kv_len
+    # the graph-replayed decode writes every row's new token to the same slot `off`; rows are right-aligned by kv_len
     # make "past" keys of each row live in slots [off - past, off)
     pos = torch.tensor([p for p in past], dtype=torch.int32)
     kv_len = torch.tensor([off + 1] * B, dtype=torch.int32)
