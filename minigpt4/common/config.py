@@ -3,6 +3,7 @@
 the used subset (`load`, `merge`, dotlist overrides, `.get`, attribute access, `to_container`) is provided by
 `Node`, a dict with attribute access."""
 import json
+import re
 
 import yaml
 
@@ -28,9 +29,21 @@ class Node(dict):
         return o
 
 
+class _Loader(yaml.SafeLoader):
+    """PyYAML follows YAML 1.1, where `1e-4` (no dot) is a string; OmegaConf — what the reference's yamls are written for —
+    reads it as a float (`init_lr: 1e-4`, `warmup_lr: 1e-6` in every train config)."""
+
+
+_Loader.add_implicit_resolver(
+    "tag:yaml.org,2002:float",
+    re.compile(r"^[-+]?(?:[0-9][0-9_]*\.[0-9_]*(?:[eE][-+]?[0-9]+)?|\.[0-9_]+(?:[eE][-+]?[0-9]+)?|[0-9][0-9_]*[eE][-+]?[0-9]+"
+               r"|\.(?:inf|Inf|INF)|\.(?:nan|NaN|NAN))$"),
+    list("-+0123456789."))
+
+
 def load_yaml(path):
     with open(path) as fh:
-        return Node.wrap(yaml.safe_load(fh) or {})
+        return Node.wrap(yaml.load(fh, Loader=_Loader) or {})
 
 
 def merge(*nodes):
@@ -52,7 +65,7 @@ def from_dotlist(opts):
         parts = key.split(".")
         for p in parts[:-1]:
             cur = cur.setdefault(p, Node())
-        cur[parts[-1]] = yaml.safe_load(val)
+        cur[parts[-1]] = yaml.load(val, Loader=_Loader)
     return out
 
 

@@ -96,7 +96,8 @@ class Myriad(Blip2Base):
         self.freeze_llama = True
         self.max_txt_len, self.end_sym = max_txt_len, end_sym
         self.vision_expert = vision_expert
-        self.llama_tokenizer = load_llama_tokenizer(llama_model, self.dims.llama.vocab)
+        synthetic = weights is not None or os.environ.get("MYRIAD_SYNTHETIC_WEIGHTS", "0") == "1"
+        self.llama_tokenizer = load_llama_tokenizer(llama_model, self.dims.llama.vocab, allow_synthetic=synthetic)
         self._frozen = self._resolve_weights(weights, llama_model, q_former_model)
         self._build_trainables()
         self.llama_model = _LlamaShim(self)
@@ -189,14 +190,27 @@ class Myriad(Blip2Base):
         def __contains__(self, k):
             return k in self.t or k in self.f
 
+    def _trainable_version(self):
+        """Changes whenever any trainable nn.Parameter was written in place (optimizer.step, load_state_dict, .copy_):
+        torch bumps a tensor's version counter on every in-place update."""
+        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+
     @property
     def engine(self):
+        """The inference engine over the CURRENT trainable weights: its prepared device copies (NHWC fp16 conv filters, LoRA
+        rows inside the fused qkv weight, ...) are refreshed in place whenever a trainable parameter changed since the last
+        use, so generate() / encode_img() after optimizer steps — e.g. the per-epoch validation of the runner — see the
+        trained weights."""
         if self._engine is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("Myriad (B200-native) needs a CUDA device; there is no CPU path")
             from myriad_b200.engine import MyriadEngine
             dev = torch.device("cuda", torch.cuda.current_device())
             self._engine = MyriadEngine(self._Merged(self._frozen, self.trainable_state()), self.dims, device=dev)
+            self._engine_version = self._trainable_version()
+        elif self._engine_version != self._trainable_version():
+            self._engine.refresh_trainables(self._Merged(self._frozen, self.trainable_state()))
+            self._engine_version = self._trainable_version()
         return self._engine
 
     # -------------------------------------------------------------------------------------- public API

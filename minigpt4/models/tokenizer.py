@@ -25,6 +25,7 @@ class SyntheticLlamaTokenizer:
         self.vocab_size = vocab_size
         self.pad_token = self.eos_token
         self.padding_side = "right"
+        self._seen = {}  # id -> piece for everything encoded so far, so decode() returns readable text for known pieces
 
     @property
     def pad_token_id(self):
@@ -49,7 +50,12 @@ class SyntheticLlamaTokenizer:
         # '###' is the stop marker of the conversation template (conversation.py:128-130): keep its real Vicuna id
         ids = []
         for p in self._pieces(text.replace("###", " \x00 ")):
-            ids.append(835 if p == "\x00" and self.vocab_size > 835 else 3 + zlib.crc32(p.encode()) % (self.vocab_size - 3))
+            if p == "\x00" and self.vocab_size > 835:
+                ids.append(835)
+                continue
+            i = 3 + zlib.crc32(p.encode()) % (self.vocab_size - 3)
+            self._seen.setdefault(i, p)
+            ids.append(i)
         return ([self.bos_token_id] if add_special_tokens else []) + ids
 
     def __call__(self, text, return_tensors=None, add_special_tokens=True, padding=False, truncation=False, max_length=None,
@@ -76,17 +82,29 @@ class SyntheticLlamaTokenizer:
         for i in ids:
             if skip_special_tokens and i in (0, 1, 2):
                 continue
-            toks.append("###" if i == 835 else "<%d>" % i)
+            toks.append("###" if i == 835 else self._seen.get(i, "<%d>" % i))
         return " ".join(toks)
 
     def batch_decode(self, batch, **kw):
         return [self.decode(r, **kw) for r in batch]
 
 
-def load_llama_tokenizer(path, vocab_size=32000):
-    if path and os.path.isdir(path) and os.path.exists(os.path.join(path, "tokenizer.model")):
-        from transformers import LlamaTokenizer
-        tok = LlamaTokenizer.from_pretrained(path, use_fast=False)
-        tok.pad_token = tok.eos_token
-        return tok
-    return SyntheticLlamaTokenizer(vocab_size)
+def load_llama_tokenizer(path, vocab_size=32000, allow_synthetic=False):
+    """The Vicuna SentencePiece tokenizer of `path` (myriad.py:181-182). The hash-based stand-in is returned ONLY when the
+    caller runs on synthetic weights (`allow_synthetic`: MYRIAD_SYNTHETIC_WEIGHTS=1 or an explicit `weights=` mapping): with a
+    real checkpoint a missing / mistyped tokenizer path must fail, not silently produce garbage prompts and decodes."""
+    if path and os.path.isdir(path):
+        if os.path.exists(os.path.join(path, "tokenizer.model")):
+            from transformers import LlamaTokenizer
+            tok = LlamaTokenizer.from_pretrained(path, use_fast=False)
+            tok.pad_token = tok.eos_token
+            return tok
+        if os.path.exists(os.path.join(path, "tokenizer.json")):
+            from transformers import AutoTokenizer
+            tok = AutoTokenizer.from_pretrained(path)
+            tok.pad_token = tok.eos_token
+            return tok
+    if allow_synthetic:
+        return SyntheticLlamaTokenizer(vocab_size)
+    raise FileNotFoundError("no LLaMA tokenizer (tokenizer.model / tokenizer.json) under llama_model=%r; the synthetic tokenizer is "
+                            "only used with MYRIAD_SYNTHETIC_WEIGHTS=1 or weights=" % (path,))

@@ -49,12 +49,16 @@ class _FusedStep(torch.autograd.Function):
         tr = _trainer_for(model)
         _sync_params_to_trainer(tr, dict(zip(keys, params)))
         loss = tr.forward_backward(image, maps, stage, ids_before, ids_after, text_ids, text_mask)
-        ctx.trainer, ctx.keys = tr, keys
+        ctx.trainer, ctx.keys, ctx.model = tr, keys, model
         ctx.devices = [p.device for p in params]
         return loss.detach().clone()
 
     @staticmethod
     def backward(ctx, grad_out):
+        world = getattr(ctx.model, "dp_world", 1)
+        if world > 1:  # data parallel (myriad_b200.dp.FlatGradDataParallel): one all-reduce of the flat buffer = DDP's mean
+            from myriad_b200.dp import mean_flat_grads_
+            mean_flat_grads_(ctx.trainer.flat_grads, world)
         grads = ctx.trainer.export_grads()  # reference layouts, already unscaled
         g = grad_out.to(ctx.trainer.dev)
         out = [(grads[k] * g).to(d) for k, d in zip(ctx.keys, ctx.devices)]

@@ -60,3 +60,32 @@ def max_over_ranks(value, device="cpu"):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class FlatGradDataParallel(torch.nn.Module):
+    """Data-parallel wrapper the runner puts around the drop-in model when `run.distributed` (the reference wraps it in torch
+    DDP with find_unused_parameters=True, runner_base.py:93-98). Exposes `.module` like DDP. It installs no per-parameter
+    hooks: the model's fused backward (minigpt4/models/train_step.py) sees `dp_world > 1` and averages the ONE flat fp32
+    gradient buffer of all trainable parameters across ranks (NCCL) before the nn.Parameter gradients are materialised, so
+    parameters a rank's randomly drawn stage did not touch contribute zeros to the mean, exactly like DDP's unused-parameter
+    handling."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+        module.dp_world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    @property
+    def device(self):
+        return self.module.device
+
+
+def mean_flat_grads_(flat, world):
+    """In-place mean over ranks of a flat gradient buffer."""
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.mul_(1.0 / world)
+    return flat

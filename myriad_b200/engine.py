@@ -112,6 +112,40 @@ class MyriadEngine:
         if self.tokw is not None:
             self.tokw.base_prompts = _f(sd["VETokenizer.base_prompts"], self.dev)
 
+    def refresh_trainables(self, sd):
+        """Re-read the TRAINABLE tensors (LoraAdaptorV2, both conv stacks + base_prompts, LoRA A / B) from `sd` into the prepared
+        device copies, in place: captured decode graphs and cached tensor maps keep pointing at live storage. Called by the
+        drop-in model after optimizer steps (the frozen ViT / Q-Former / LLaMA operands are never touched)."""
+        with torch.no_grad():
+            W = self.vitw
+            W.ad1.copy_(sd["expert_adaptor.conv1.weight"])
+            W.ad2.copy_(sd["expert_adaptor.conv2.weight"])
+            for mod, cur, head_k in (("VEInstructor", self.instw, 1), ("VETokenizer", self.tokw, 5)):
+                if cur is None:
+                    continue
+                new = self._prep_conv(sd, mod, head_k)
+                for (a, ab, _, _), (b, bb, _, _) in zip(cur.direct + cur.gemm, new.direct + new.gemm):
+                    a.copy_(b)
+                    ab.copy_(bb)
+                cur.head_w.copy_(new.head_w)
+                cur.head_b.copy_(new.head_b)
+            if self.tokw is not None:
+                self.tokw.base_prompts.copy_(sd["VETokenizer.base_prompts"])
+            r, D = self.d.lora_r, self.d.llama.hidden
+            if r > 0:
+                for i, L in enumerate(self.llw.layers):
+                    pl = "llama_model.base_model.model.model.layers.%d.self_attn." % i
+                    a = torch.cat([sd[pl + "q_proj.lora_A.default.weight"], sd[pl + "v_proj.lora_A.default.weight"]])
+                    bq, bv = sd[pl + "q_proj.lora_B.default.weight"], sd[pl + "v_proj.lora_B.default.weight"]
+                    if self.FUSED_LLAMA:
+                        L.wqkv[3 * D:3 * D + 2 * r].copy_(a)
+                        L.lora.bq.copy_(bq)
+                        L.lora.bv.copy_(bv)
+                    else:
+                        L.lora.a.copy_(a)
+                        L.lora.bq.copy_(bq * L.lora.scale)
+                        L.lora.bv.copy_(bv * L.lora.scale)
+
     def _prep_qformer(self, sd):
         q, dev = self.d.qf, self.dev
         p = "Qformer.bert."

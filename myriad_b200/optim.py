@@ -82,14 +82,32 @@ def no_weight_decay(name, ndim):
     return ndim < 2 or "bias" in name or "ln" in name or "bn" in name
 
 
+def _is_main_process():
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+
 def save_checkpoint(trainer, path, epoch, config=None, scaler=None):
     """runner_base.py:592-628: only parameters with requires_grad are stored under "model" (reference key names and layouts,
-    so `Myriad.load_state_dict(strict=False)` and the reference's own `ckpt:` loader read it)."""
+    so `Myriad.load_state_dict(strict=False)` and the reference's own `ckpt:` loader read it). Rank 0 writes (the reference
+    guards `_save_checkpoint` with @main_process); the other ranks return the path without touching the file system.
+
+    "model", "config", "scaler", "epoch" follow the reference layout. "optimizer" does NOT: it is the fused optimizer's own
+    record (kind = "myriad_b200.fused_adamw": step count, hyper-parameters, loss scale, flat AdamW moments by parameter
+    name), which torch.optim.AdamW.load_state_dict cannot read — a checkpoint written here resumes through load_checkpoint
+    below, and its "model" entry loads anywhere."""
+    if not _is_main_process():
+        return path
+    if scaler is None:
+        scaler = getattr(trainer, "scaler", None)
+    if hasattr(trainer, "sync_loss_scale"):
+        trainer.sync_loss_scale()
     names = list(trainer.segments.keys())
     obj = {
         "model": {k: v.cpu() for k, v in trainer.export_state_dict().items()},
         # flat AdamW moments by parameter name (same layouts as "model"); step counts the optimizer steps taken
         "optimizer": {"kind": "myriad_b200.fused_adamw", "step": trainer.opt_step, "hyper": dict(trainer.hp),
+                      "loss_scale": float(trainer.loss_scale),
                       "exp_avg": {k: v.cpu() for k, v in trainer.export_flat(trainer.exp_avg).items()},
                       "exp_avg_sq": {k: v.cpu() for k, v in trainer.export_flat(trainer.exp_avg_sq).items()},
                       "param_names": names},
@@ -106,13 +124,60 @@ def save_checkpoint(trainer, path, epoch, config=None, scaler=None):
 def load_checkpoint(trainer, path, scaler=None):
     """runner_base.py:649-672: restores the trainable parameters, the optimizer state and the scaler; returns the epoch to
     resume from (stored epoch + 1)."""
+    import warnings
     ck = torch.load(path, map_location="cpu", weights_only=False)
+    missing = [k for k in trainer.segments if k not in ck["model"]]
+    if missing:
+        warnings.warn("checkpoint %s lacks %d trainable tensors (kept at their current values): %s ..." % (path, len(missing), missing[:3]))
     trainer.import_state_dict(ck["model"])
     opt = ck.get("optimizer")
     if isinstance(opt, dict) and opt.get("kind") == "myriad_b200.fused_adamw":
         trainer.opt_step = int(opt["step"])
+        trainer.hp.update(opt.get("hyper", {}))
         trainer.import_flat(trainer.exp_avg, opt["exp_avg"])
         trainer.import_flat(trainer.exp_avg_sq, opt["exp_avg_sq"])
-    if scaler is not None and ck.get("scaler"):
-        scaler.load_state_dict(ck["scaler"])
+        if "loss_scale" in opt:
+            trainer.loss_scale = float(opt["loss_scale"])
+    elif isinstance(opt, dict) and "state" in opt and "param_groups" in opt:
+        n = import_torch_adamw_state(trainer, opt, ck["model"])
+        if n == 0:
+            warnings.warn("checkpoint %s: torch AdamW state could not be matched to the trainable tensors; the optimizer restarts cold" % path)
+    else:
+        warnings.warn("checkpoint %s carries no usable optimizer state (kind %r): AdamW moments and step restart from zero"
+                      % (path, opt.get("kind") if isinstance(opt, dict) else type(opt).__name__))
+    if ck.get("scaler"):
+        for sc in (scaler, getattr(trainer, "scaler", None)):
+            if sc is not None:
+                sc.load_state_dict(ck["scaler"])
+        if hasattr(trainer, "scaler") and not (isinstance(opt, dict) and "loss_scale" in opt):
+            trainer.loss_scale = float(trainer.scaler.scale)
+    if hasattr(trainer, "scaler"):
+        trainer.scaler.scale = trainer.loss_scale
     return int(ck.get("epoch", -1)) + 1
+
+
+def import_torch_adamw_state(trainer, opt_state, model_state):
+    """A checkpoint written by the reference runner (runner_base.py:606 `optimizer.state_dict()` of torch.optim.AdamW over the
+    parameters with requires_grad, in named_parameters() order = the order of its "model" entry): copy exp_avg / exp_avg_sq /
+    step into the flat buffers. Parameters are matched by position and checked by shape. Returns how many were imported."""
+    keys = [k for k in model_state if k in trainer.segments]
+    ids = [i for g in opt_state["param_groups"] for i in g["params"]]
+    st = opt_state["state"]
+    if len(ids) != len(keys):
+        # the runner lists decayed parameters first, then the un-decayed ones (runner_base.py:111-133)
+        return 0
+    decayed = [k for k in keys if not no_weight_decay(k, model_state[k].ndim)]
+    ordered = decayed + [k for k in keys if k not in decayed]
+    m, v, n, step = {}, {}, 0, 0
+    for pid, key in zip(ids, ordered):
+        rec = st.get(pid)
+        if rec is None or tuple(rec["exp_avg"].shape) != tuple(model_state[key].shape):
+            continue
+        m[key], v[key] = rec["exp_avg"], rec["exp_avg_sq"]
+        step = max(step, int(rec["step"]))
+        n += 1
+    if n:
+        trainer.import_flat(trainer.exp_avg, m)
+        trainer.import_flat(trainer.exp_avg_sq, v)
+        trainer.opt_step = step
+    return n

@@ -45,6 +45,15 @@ class MyriadTrainer(MyriadEngine):
         self.exp_avg_sq = torch.zeros_like(self.flat_params)
         self.found_inf = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self._saved = None
+        # GradScaler semantics for the internal fp16 backward (runner_base.py:141-149): the scale every weight-gradient epilogue
+        # divides out again is driven by the device-side inf / nan flag of the optimizer step. The flag is read back without
+        # stalling the launch queue (pinned copy + event, examined one step later); a skipped step is taken back out of
+        # opt_step so AdamW's bias correction counts applied updates only, like torch.optim.AdamW under GradScaler.step.
+        from .optim import DynamicLossScale
+        self.scaler = DynamicLossScale(init_scale=self.loss_scale)
+        self._flag_ring = [(torch.zeros(1, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)] if self.dev.type == "cuda" else []
+        self._flag_pending = []
+        self.skipped_steps = 0
 
     # ------------------------------------------------------------------------------- flat parameter space
     def _prep_experts(self, sd):
@@ -626,11 +635,40 @@ class MyriadTrainer(MyriadEngine):
         (runner_base.py:105-139) + refresh of the fp16 operand copies."""
         from .dp import allreduce_flat_grads
         mean_scale = allreduce_flat_grads(self.flat_grads)  # sum over ranks; 1 / world folded into the optimizer's unscale
+        self._poll_overflow_flags(block=len(self._flag_pending) >= len(self._flag_ring))
         self.opt_step += 1
         hp = self.hp
         K.adamw_step(self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq, self.wd_mask, hp["lr"] if lr is None else lr,
                      hp["beta1"], hp["beta2"], hp["eps"], hp["wd"], self.opt_step, inv_scale=mean_scale, found_inf=self.found_inf)
+        if self._flag_ring:
+            host, ev = self._flag_ring[(self.opt_step + self.skipped_steps) % len(self._flag_ring)]
+            host.copy_(self.found_inf, non_blocking=True)
+            ev.record()
+            self._flag_pending.append((host, ev))
         self.refresh_trainables()
+
+    def _poll_overflow_flags(self, block=False):
+        """Fold finished steps' inf / nan flags into the loss scale (x0.5 and the step un-counted on overflow, x2 after 2000
+        clean steps). `block` waits for the oldest outstanding flag (used when the small ring is full, and by sync_loss_scale)."""
+        while self._flag_pending:
+            host, ev = self._flag_pending[0]
+            if not ev.query():
+                if not block:
+                    break
+                ev.synchronize()
+            self._flag_pending.pop(0)
+            bad = bool(int(host[0]))
+            if bad:
+                self.opt_step -= 1
+                self.skipped_steps += 1
+            self.loss_scale = float(self.scaler.update(bad))
+            block = False
+
+    def sync_loss_scale(self):
+        """Wait for every outstanding overflow flag (before a checkpoint is written / when a test inspects the scale)."""
+        while self._flag_pending:
+            self._poll_overflow_flags(block=True)
+        return self.loss_scale
 
     def train_step(self, image, maps, stage, ids_before, ids_after, text_ids, text_mask, lr=None):
         loss = self.forward_backward(image, maps, stage, ids_before, ids_after, text_ids, text_mask)
