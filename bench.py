@@ -80,13 +80,41 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+QUESTION = ("<Img><ImageHere></Img> This image may be simulated by photo editing According to IAD expert opinions and corresponding visual "
+            "descriptions find out if there are defects")
+
+
+def _questions(tokenizer, n_after=26):
+    """A question string whose wrapped prompt '###Human: <Img>' + image + '</Img> ... ###Assistant: ' tokenises to 6 + 26 = 32
+    prompt tokens (north_star: 32-token prompts) under the tokenizer in use; words are dropped / repeated to hit the count."""
+    words = QUESTION.split(" ")
+    head, tail = words[0], words[1:]
+
+    def n_tok(ws):
+        text = "###Human: " + " ".join([head] + ws) + " ###Assistant: "
+        after = text.split("<ImageHere>")[1]
+        return tokenizer(after, return_tensors="pt", add_special_tokens=False).input_ids.shape[1]
+
+    ws = list(tail)
+    while n_tok(ws) > n_after and ws:
+        ws.pop()
+    while n_tok(ws) < n_after:
+        ws.append("defects")
+    assert n_tok(ws) == n_after, "cannot build a %d-token prompt tail" % n_after
+    return " ".join([head] + ws)
+
+
 def run_ours(args):
+    import zlib
+
     import torch
     import torch.distributed as dist
 
+    import minigpt4.models  # noqa: F401  (registers arch: myriad)
+    from minigpt4.common.registry import registry
+    from minigpt4.conversation.conversation import StoppingCriteriaSub
     from myriad_b200 import kernels as K
     from myriad_b200 import synthetic as syn
-    from myriad_b200.engine import MyriadEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -97,23 +125,32 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     dims = syn.full_dims(lora_r=8)
     t0 = time.time()
-    eng = MyriadEngine(syn.LazyStateDict(dims, seed=0, device=dev), dims, device=dev, max_batch=BATCH, max_seq=256)
+    # the reference-facing plugin: the registry-registered class, built the way evaluation_aqa_dataset.py:255-256 builds it
+    model = registry.get_model_class("myriad")(use_lora=True, llama_model="", max_txt_len=32, end_sym="###",
+                                                weights=syn.LazyStateDict(dims, seed=0, device=dev)).to(dev).eval()
+    eng = model.engine
     torch.cuda.synchronize()
     t_load = time.time() - t0
     image, maps = syn.make_inputs(BATCH, seed=1234 + rank, device="cpu")
     image_h, maps_h = image.pin_memory(), maps.pin_memory()
     image_d, maps_d = image_h.to(dev), maps_h.to(dev)
-    ids_b, ids_a = syn.make_prompt_ids(dims.llama.vocab)
+    question = _questions(model.llama_tokenizer)
+    samples_h = {"image": image_h, "anomaly_maps": maps_h, "question": [question] * BATCH, "question2": [question] * BATCH,
+                 "question3": [question] * BATCH, "scene": ["bottle"] * BATCH, "img_path": ["synthetic/%d.png" % i for i in range(BATCH)]}
     stops = ((835,), (2277, 29937))
+    crit = [StoppingCriteriaSub(stops=[torch.tensor(s) for s in stops])]
+    gen_kw = dict(max_new_tokens=NEW_TOKENS, stopping_criteria=crit, do_sample=True, top_p=0.01, temperature=1.0, min_length=1, use_cache=True)
+    ids_b, ids_a = model._split_prompts(["###Human: " + question + " ###Assistant: "], dev)
+    ids_b, ids_a = ids_b[0], ids_a[0]
+    assert ids_b.numel() + ids_a.numel() == 32, (ids_b.numel(), ids_a.numel())
 
     def step_resident():
         return eng.generate(image_d, maps_d, ids_b, ids_a, max_new_tokens=NEW_TOKENS, stop_seqs=stops)
 
     def step_e2e():
-        # the call a user makes: host batch in (pinned), token ids out on the host
-        im = image_h.to(dev, non_blocking=True)
-        mp = maps_h.to(dev, non_blocking=True)
-        return eng.generate(im, mp, ids_b, ids_a, max_new_tokens=NEW_TOKENS, stop_seqs=stops)
+        # the call a user of the reference makes (evaluation_aqa_dataset.py:333): host batch + question strings in, token ids out
+        out = model.generate(samples_h, **gen_kw)
+        return out["token_ids"].cpu()
 
     def barrier():
         if world > 1:
@@ -125,9 +162,10 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = K.launch_count()
         e0.record()
-        ntok = 0
+        ntok, last = 0, None
         for _ in range(steps):
-            ntok += fn().numel()
+            last = fn()
+            ntok += last.numel()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -135,13 +173,13 @@ def run_ours(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, ntok, K.launch_count() - n0
+        return ms, ntok, K.launch_count() - n0, last
 
     if args.profile:  # under ncu: one warm-up (graph capture), one step, nothing else
         step_resident()
         torch.cuda.synchronize()
         torch.cuda.profiler.start()  # ncu --profile-from-start off: only the one step below is captured
-        ms, ntok, launches = timed(step_resident, 1)
+        ms, ntok, launches, _ = timed(step_resident, 1)
         torch.cuda.profiler.stop()
         print(json.dumps({"profile_run": True, "ms_per_step_under_profiler": ms, "gpu_launches": launches}), flush=True)
         return
@@ -150,22 +188,32 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, ntok, launches = timed(step_resident, args.steps)
+    eng.decode_timing = []
+    ms, ntok, launches, toks_timed = timed(step_resident, args.steps)
+    decode_events, eng.decode_timing = eng.decode_timing, None
     clocks = sampler.stop() if rank == 0 else None
     step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    ms_e2e, _, _, toks_e2e = timed(step_e2e, args.steps)
+
+    # correctness of the timed run: the graph-replayed decode must reproduce an eager (un-graphed) replay of the same launches
+    # bit for bit, and the plugin call must produce the same ids as the engine call it wraps
+    emb = eng.build_inputs_embeds(image_d, maps_d, 1, ids_b, ids_a)
+    toks_eager = eng.greedy_decode(emb, NEW_TOKENS, stops, use_graph=False)
+    assert toks_timed.tolist() == toks_eager.tolist(), "timed (CUDA-graph) tokens differ from the eager replay"
+    assert toks_e2e.tolist() == toks_timed.tolist(), "plugin generate() tokens differ from the engine's"
+    checksum = "%08x" % (zlib.crc32(toks_timed.numpy().astype("int64").tobytes()) & 0xFFFFFFFF)
 
     value = world * BATCH * args.steps / (ms / 1e3)
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
-    train = None
-    if not args.no_train:
-        train = run_train_leg(args, dims, dev, world, rank, barrier)
     peaks = _peaks()
     extra = {}
     roof = None
     if rank == 0:
-        roof, extra = roofline_probe(eng, dims, dev, peaks)
-    cpu = None
+        roof, extra = roofline_in_situ(eng, dims, dev, peaks, decode_events, toks_timed.shape[1])
+    train = None
+    if not args.no_train:
+        train = run_train_leg(args, dims, dev, world, rank, barrier)
+    cpu = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import CpuSample
         torch.set_num_threads(os.cpu_count() or 1)
@@ -173,18 +221,39 @@ def run_ours(args):
         v, parts = cs.run(NEW_TOKENS)
         cpu = {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port", "sample": cs.describe(NEW_TOKENS),
                "parts_s": {k: round(x, 4) for k, x in parts.items()}}
+        cpu.update(cs.extrapolation(NEW_TOKENS))
+        del cs
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        try:
+            from oracle.cpu_baseline import EagerGpuSample
+            del model, eng
+            torch.cuda.empty_cache()
+            es = EagerGpuSample(dev)
+            ev, ems, n_new = es.time(steps=3, warmup=1, new_tokens=NEW_TOKENS)
+            eager = {"value": ev, "unit": "images/s", "ms_per_step": ems, "new_tokens": n_new,
+                     "what": "the path being replaced: the same workload through plain PyTorch eager fp16 on this B200 (oracle port on "
+                             ".half().cuda() tensors: cuBLAS / ATen kernels, torch.cat KV cache, per-step host sync of the HF greedy loop); "
+                             "pinned host images in, token ids out — comparable with e2e"}
+            del es
+        except Exception as e:
+            eager = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if rank == 0:
+        cfg = {"workload": "myriad_generate_b4", "model": "Myriad: EVA-ViT-g + Q-Former(81q) + Vicuna-7B LoRA r=8",
+               "batch_per_gpu": BATCH, "global_batch": BATCH * world, "prompt_tokens": 32, "prefill_len": 131,
+               "new_tokens": NEW_TOKENS, "parallelism": "dp%d replicas, no data-path collective" % world,
+               "l2": "inputs larger than L2: every step streams 13.5 GB of weights through a 126 MB L2",
+               "tokens_checksum": checksum, "tokens_verified": "timed CUDA-graph run == eager replay == plugin generate()"}
+        if train and "value" in train:  # second half of BASELINE.json's metric, kept inside `config` so result parsers keep it
+            cfg["train_tokens_per_s"] = train["value"]
+            cfg["train_ms_per_step"] = train["ms_per_step"]
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp16 (fp32 accumulate / residual / softmax)", "data": "synthetic",
-            "config": {"workload": "myriad_generate_b4", "model": "Myriad: EVA-ViT-g + Q-Former(81q) + Vicuna-7B LoRA r=8",
-                       "batch_per_gpu": BATCH, "global_batch": BATCH * world, "prompt_tokens": 32, "prefill_len": 131,
-                       "new_tokens": NEW_TOKENS, "parallelism": "dp%d replicas, no data-path collective" % world,
-                       "l2": "inputs larger than L2: every step streams 13.5 GB of weights through a 126 MB L2"},
+            "dtype": "fp16 (fp32 accumulate / residual / softmax)", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": image_h.numel() * 4 + maps_h.numel() * 4,
-                    "d2h_bytes_per_step": BATCH * NEW_TOKENS * 4 + 8 * NEW_TOKENS, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                    "d2h_bytes_per_step": BATCH * NEW_TOKENS * 8 + 8 * NEW_TOKENS, "ms_per_step": ms_e2e / args.steps,
+                    "api": "registry.get_model_class('myriad')(...).generate(samples) with pinned host tensors and question strings"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
             "new_tokens_per_s": ntok / (ms / 1e3) * world, "weights_load_s": round(t_load, 1),
             "train": train,
         }
@@ -249,70 +318,114 @@ def run_train_leg(args, dims, dev, world, rank, barrier):
         return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
 
-def roofline_probe(eng, dims, dev, peaks):
-    """Dominant kernel = the small-batch weight-streaming kernel (csrc/gemv.cu, `gemv_kernel`): ~75 % of a step is the 32
-    decode steps, each streaming every LLaMA weight once through 4 launches per layer. Timed live with CUDA events over the
-    real 32 layers' weights in layer order and in the decode step's own launch configuration (RMSNorm hand-over, in-place
-    fp32 residual, SwiGLU epilogue; 13 GB >> L2, so nothing is re-served from cache). Also reports the tensor-bound
-    ViT GEMM for context."""
+def _ncu_traffic(kernel="gemv_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, averaged over the launches in the committed
+    `ncu --set full` capture profiles/r2_ncu_raw.csv (written by scripts/gpu_round.sh from the same decode-step launch
+    configuration). None when the capture is absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r2_ncu_raw.csv")
+    if not os.path.exists(path):
+        return None, None
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        unit_r, unit_w = rows[1][ir], rows[1][iw]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[ir]) * mult.get(unit_r, 1.0) + float(r[iw]) * mult.get(unit_w, 1.0) for r in rows[2:] if r[ik].startswith(kernel)]
+        return (sum(vals) / len(vals), len(vals)) if vals else (None, 0)
+    except Exception:
+        return None, None
+
+
+def roofline_in_situ(eng, dims, dev, peaks, decode_events, new_tokens):
+    """Dominant kernel = the small-batch weight-streaming kernel (csrc/gemv.cu `gemv_kernel`): ~75 % of a step is the decode
+    steps, each streaming every LLaMA weight once through 4 launches per layer + lm_head. Measured where the time is spent:
+      * frac_step: (weight + KV-cache bytes of one decode step) / decode-step time, the step time taken with CUDA events
+        around the graph replays INSIDE the timed region of the benchmark (engine.decode_timing);
+      * frac (kernel): algorithmic bytes of the 129 gemv launches of one decode step / the sum of their durations inside
+        the captured step, each launch timed by its own CTAs (%globaltimer: from the moment its predecessor released it,
+        griddepcontrol.wait returning, to its last CTA done) — attention, arg-max and the launch boundaries are outside."""
+    import ctypes
+
     import torch
 
     from myriad_b200 import kernels as K
     l = dims.llama
     B = BATCH
-    x = torch.randn(B, l.hidden, device=dev).half()
-    a = torch.randn(B, l.inter, device=dev).half()
     wq = eng.llw.layers[0].wqkv.shape[0]  # 3 * hidden + 2 * lora_r (LoRA A rows ride along)
-    qkv = torch.empty(B, wq, device=dev, dtype=torch.float16)
-    o = torch.zeros(B, l.hidden, device=dev, dtype=torch.float32)
-    act = torch.empty(B, l.inter, device=dev, dtype=torch.float16)
-    fused = eng.fuse_small_batch_norm and B <= 4
-
-    ya, yb = (torch.zeros(B, l.hidden, device=dev, dtype=torch.float16) for _ in range(2))
-    ssa, ssb = (torch.zeros(K.NORM_SS_FLOATS, device=dev) for _ in range(2))
-
-    def sweep():
-        for L in eng.llw.layers:
-            if fused:  # the decode step's own launch configuration: RMSNorm handed over between the projections
-                K.gemm(yb, L.wqkv, out=qkv, w_static=True, norm_ss=(ssb, l.eps))
-                K.gemm(x, L.wo, res=o, out=o, w_static=True, post_norm=(L.n2, ya, ssa))
-                K.gemm(ya, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True, norm_ss=(ssa, l.eps))
-                K.gemm(a, L.wd, res=o, out=o, w_static=True, post_norm=(L.n1, yb, ssb))
-            else:
-                K.gemm(x, L.wqkv, out=qkv, w_static=True)
-                K.gemm(x, L.wo, res=o, out=o, w_static=True)
-                K.gemm(x, L.wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
-                K.gemm(a, L.wd, res=o, out=o, w_static=True)
-
-    for _ in range(2):
-        sweep()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    o.zero_()
-    e0.record()
-    for _ in range(reps):
-        sweep()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    n_launch = 4 * l.layers
-    wbytes = l.layers * 2 * (wq * l.hidden + l.hidden * l.hidden + 2 * l.inter * l.hidden + l.hidden * l.inter)
+    w_layer = 2 * (wq * l.hidden + l.hidden * l.hidden + 2 * l.inter * l.hidden + l.hidden * l.inter)
+    w_head = 2 * l.vocab * l.hidden
     # activations per layer: fp16 rows in (3 x hidden + inter), fp32 residual read + written by o / down, their fp16 hand-over
     # rows + gamma, qkv / act written in fp16
-    abytes = l.layers * (B * 2 * (3 * l.hidden + l.inter) + 2 * 2 * B * 4 * l.hidden + 2 * (B * 2 * l.hidden + 4 * l.hidden) +
-                         B * 2 * wq + B * 2 * l.inter)
-    per_launch = (wbytes + abytes) / n_launch
-    achieved = (wbytes + abytes) / (ms / 1e3) / 1e9
-    kname = "gemv_kernel" if fused else "gemm_tc_kernel"
-    roof = {"kernel": "%s (decode, T=%d: norm+qkv+loraA / o+res / norm+gate_up+swiglu / down+res of all 32 layers)" % (kname, B), "bound": "hbm",
+    a_layer = (B * 2 * (3 * l.hidden + l.inter) + 2 * 2 * B * 4 * l.hidden + 2 * (B * 2 * l.hidden + 4 * l.hidden) + B * 2 * wq + B * 2 * l.inter)
+    gemv_bytes = l.layers * (w_layer + a_layer) + w_head + B * 2 * l.hidden + B * 4 * l.vocab
+    n_gemv = 4 * l.layers + 1
+    # ---- decode-step time inside the timed region
+    torch.cuda.synchronize()
+    tot_ms = sum(e0.elapsed_time(e1) for e0, e1, n in decode_events)
+    tot_steps = sum(n for _, _, n in decode_events)
+    step_ms = tot_ms / max(tot_steps, 1)
+    S_mid = 131 + new_tokens // 2
+    kv_bytes = 2 * l.layers * B * S_mid * l.hidden * 2  # K and V rows of the visible cache, fp16, mid-generation
+    embed_bytes = B * l.hidden * 2
+    step_bytes = l.layers * w_layer + w_head + kv_bytes + embed_bytes
+    frac_step = step_bytes / (step_ms / 1e3) / 1e9 / peaks["hbm"] if step_ms > 0 else None
+    # ---- per-launch durations from inside one captured decode step
+    st = next(iter(eng._decode_graphs.values()))
+    fused = st.graph is not None and eng.fuse_small_batch_norm and B <= 4 and st.mega is None
+    kernel_us = None
+    if fused:
+        n_slots = n_gemv + 8
+        buf = torch.zeros(n_slots * 148 * 6, dtype=torch.int64, device=dev)
+        snap = st.state.clone()
+        K.lib().myr_gemm_set_trace(ctypes.c_void_p(buf.data_ptr()))
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                eng._decode_step(st)
+        finally:
+            K.lib().myr_gemm_set_trace(ctypes.c_void_p(0))
+        st.state.copy_(snap)
+        g.replay()
+        g.replay()  # timestamps of the second replay (warm instruction cache) overwrite the first
+        torch.cuda.synchronize()
+        st.state.copy_(snap)
+        t = buf.reshape(n_slots, 148, 6)[:n_gemv].cpu()
+        live = t[:, :, 5] > 0
+        durs = []
+        for i in range(n_gemv):
+            m = live[i]
+            if m.any():
+                durs.append((int(t[i, m, 5].max()) - int(t[i, m, 1].min())) / 1e3)
+        if len(durs) == n_gemv:
+            kernel_us = sum(durs)
+    traffic, n_cap = _ncu_traffic()
+    if kernel_us:
+        achieved = gemv_bytes / (kernel_us / 1e6) / 1e9
+        avg_us = kernel_us / n_gemv
+    else:  # tensor-core weight streaming path (MYR_GEMV=0 / MYR_MEGA=1): only the step-level figure is available
+        achieved = step_bytes / (step_ms / 1e3) / 1e9
+        avg_us = None
+    roof = {"kernel": "gemv_kernel (decode, T=%d: norm+qkv+loraA / o+res / norm+gate_up+swiglu / down+res of all 32 layers + lm_head), timed "
+                      "inside the captured decode step" % B, "bound": "hbm",
             "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four launches of a layer, from the committed
-            # `ncu --set full` capture of these launches (profiles/r1_ncu_full_pass3.md rows 0-3: 90.38 + 3.66, 100.87 + 3.67,
-            # 33.70 + 0.00, 180.43 + 3.41 MB); not re-measured by this run
-            "traffic": 104.03e6 if fused else None,
-            "peak_source": peaks["src"], "avg_launch_us": ms * 1e3 / n_launch, "algorithmic_bytes_per_launch": per_launch}
-    # tensor-bound context: the ViT MLP GEMMs at the bench batch (T = B * 257)
+            "frac_step": frac_step, "decode_step_ms": step_ms, "decode_steps_timed": tot_steps, "step_bytes": step_bytes,
+            "traffic": traffic, "traffic_source": ("profiles/r2_ncu_raw.csv: mean dram read+write of %d gemv_kernel launches under ncu --set full" % n_cap)
+            if traffic else None,
+            "peak_source": peaks["src"], "avg_launch_us": avg_us, "launches_per_step": n_gemv,
+            "algorithmic_bytes_per_launch": gemv_bytes / n_gemv}
+    return roof, tensor_context(eng, dims, dev, peaks)
+
+
+def tensor_context(eng, dims, dev, peaks):
+    """Tensor-bound context kernels (north_star: tensor-pipe share of the GEMM / attention kernels): the ViT MLP GEMM and the ViT
+    flash-attention launch at the bench batch, back to back over the 39 layers' own weights."""
+    import torch
+
+    from myriad_b200 import kernels as K
+    B = BATCH
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     T, D, Hd = B * dims.vit.tokens, dims.vit.dim, dims.vit.mlp_hidden
     h = torch.randn(T, D, device=dev).half()
     m = torch.empty(T, Hd, device=dev, dtype=torch.float16)
@@ -320,14 +433,18 @@ def roofline_probe(eng, dims, dev, peaks):
     for b in blk[:3]:
         K.gemm(h, b.fc1w, bias=b.fc1b, act=K.ACT_GELU, out=m)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()  # launches back to back on the device: a 10 us GEMM is shorter than the host's launch path
+    with torch.cuda.graph(g):
+        for b in blk:
+            K.gemm(h, b.fc1w, bias=b.fc1b, act=K.ACT_GELU, out=m)
+    g.replay()
+    torch.cuda.synchronize()
     e0.record()
-    for b in blk:
-        K.gemm(h, b.fc1w, bias=b.fc1b, act=K.ACT_GELU, out=m)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     ms2 = e0.elapsed_time(e1) / len(blk)
     tf = 2.0 * T * D * Hd / (ms2 / 1e3) / 1e12
-    # attention context (north_star: tensor-pipe share of the attention kernels): the ViT flash-attention launch at the bench batch
     v = dims.vit
     qkv_a = torch.randn(T, 3 * D, device=dev).half()
     ctx_a = torch.empty(T, D, device=dev, dtype=torch.float16)
@@ -340,21 +457,24 @@ def roofline_probe(eng, dims, dev, peaks):
     for _ in range(3):
         attn_once()
     torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        for _ in range(20):
+            attn_once()
+    g2.replay()
+    torch.cuda.synchronize()
     e0.record()
-    for _ in range(20):
-        attn_once()
+    g2.replay()
     e1.record()
     torch.cuda.synchronize()
     ms3 = e0.elapsed_time(e1) / 20
     tf_a = 4.0 * B * v.heads * v.tokens * v.tokens * v.head_dim / (ms3 / 1e3) / 1e12
-    extra_attn = {"kernel": "attn_fwd_kernel (ViT, B=%d H=%d N=%d dh=%d)" % (B, v.heads, v.tokens, v.head_dim), "bound": "tensor",
-                  "achieved": tf_a, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": tf_a / peaks["tensor"], "avg_launch_us": ms3 * 1e3,
-                  "note": "latency-bound at this size (1.5 GFLOP per launch, 1 % of the step); tensor pipe 7 % active in profiles/"}
-    extra = {"roofline_attention": extra_attn,
-             "roofline_tensor": {"kernel": "gemm_tc_kernel (ViT fc1+GELU, T=%d F=%d K=%d)" % (T, Hd, D), "bound": "tensor",
-                                 "achieved": tf, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": tf / peaks["tensor"],
-                                 "avg_launch_us": ms2 * 1e3}}
-    return roof, extra
+    return {"roofline_attention": {"kernel": "attn_fwd_kernel (ViT, B=%d H=%d N=%d dh=%d)" % (B, v.heads, v.tokens, v.head_dim), "bound": "tensor",
+                                   "achieved": tf_a, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": tf_a / peaks["tensor"],
+                                   "avg_launch_us": ms3 * 1e3},
+            "roofline_tensor": {"kernel": "ViT fc1+GELU GEMM (T=%d F=%d K=%d), 39 layers' weights back to back" % (T, Hd, D), "bound": "tensor",
+                                "achieved": tf, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": tf / peaks["tensor"],
+                                "avg_launch_us": ms2 * 1e3}}
 
 
 def run_reference(args):
@@ -369,7 +489,7 @@ def run_reference(args):
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every host core
     cs = CpuSample()
     vals = []
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 2))
     for _ in range(min(args.warmup, 1)):
         cs.run(NEW_TOKENS)
     for _ in range(steps):
@@ -381,8 +501,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "fp32 (CPU)", "data": "synthetic",
             "config": {"workload": "myriad_generate_b4", "batch_per_gpu": BATCH, "prompt_tokens": 32, "prefill_len": 131,
                        "new_tokens": NEW_TOKENS},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": cs.describe(NEW_TOKENS)},
+            "cpu_baseline": dict({"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                  "sample": cs.describe(NEW_TOKENS)}, **cs.extrapolation(NEW_TOKENS)),
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -395,6 +515,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train tokens/s)")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager fp16 GPU baseline of the same workload")
     ap.add_argument("--profile", action="store_true", help="minimal run for ncu (numbers printed under a profiler are not bench values)")
     args = ap.parse_args()
     if args.impl == "reference":

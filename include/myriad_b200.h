@@ -274,6 +274,14 @@ int myr_norm_bwd(const void* x, int64_t ldx, const void* dy, int32_t dy_dtype, i
                  int64_t ldo16, void* stream);
 int myr_swiglu_bwd(const void* gate_up, int64_t ld_gu, const void* dact, int64_t ld_da, void* dgu, int64_t ld_dgu, int32_t T,
                    int32_t I, void* stream);
+/* LoRA dropout (peft lora_dropout = 0.05, reference myriad.py:175; applied to the input of each LoRA branch while training).
+ * Counter-based: element i of [rows, D] is kept iff hash(seed, offset + i) >= p * 2^32 and scaled by 1 / (1 - p); the backward
+ * (acc += mask * g / (1 - p)) regenerates the mask from the same (seed, offset). myr_dropout_mask exports the 0/1 mask. */
+int myr_dropout_fwd(const void* x_f16, int64_t ldx, void* out_f16, int64_t ldo, int32_t rows, int32_t D, float p, uint64_t seed,
+                    uint64_t offset, void* stream);
+int myr_dropout_bwd_add(const void* g_f32, int64_t ldg, void* acc_f32, int64_t lda, int32_t rows, int32_t D, float p, uint64_t seed,
+                        uint64_t offset, void* stream);
+int myr_dropout_mask(void* out_u8, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
 int myr_gelu_fwd(const void* pre, void* out, int64_t n, void* stream);
 int myr_gelu_bwd(const void* pre, const void* dy, void* dpre, int64_t n, void* stream);
 int myr_rope_bwd(void* dqkv, int64_t ld, int32_t T, int32_t H, int32_t dh, const void* pos, const void* cos_table,

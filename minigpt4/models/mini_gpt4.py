@@ -10,6 +10,7 @@ from minigpt4.models.myriad import Myriad
 @registry.register_model("mini_gpt4")
 class MiniGPT4(Myriad):
     PRETRAINED_MODEL_CONFIG_DICT = {"pretrain_vicuna": "configs/models/minigpt4.yaml"}
+    GENERATE_STAGE = 3  # no expert tokens: [32 Q-Former queries] only
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -29,3 +30,7 @@ class MiniGPT4(Myriad):
         z = torch.zeros(image.shape[0], 1, 224, 224, device=image.device)
         q = samples.get("question", None)
         return image, q, samples.get("text_input", None), z, z
+
+    def forward(self, samples):
+        raise NotImplementedError("plain MiniGPT-4 trains llama_proj (mini_gpt4.py:180-257), which the Myriad finetune keeps frozen; "
+                                  "only its inference path (encode_img / generate / Chat) is built on this hot path")

@@ -72,6 +72,7 @@ class _LlamaShim:
 @registry.register_model("myriad")
 class Myriad(Blip2Base):
     PRETRAINED_MODEL_CONFIG_DICT = {"pretrain_vicuna": "configs/models/minigpt4.yaml"}
+    GENERATE_STAGE = 1  # Myriad.generate always encodes with stage 1 (myriad.py:435): VEInstructor queries + VETokenizer tokens
 
     def __init__(self, vit_model="eva_clip_g", q_former_model="", img_size=224, drop_path_rate=0, use_grad_checkpoint=False,
                  vit_precision="fp16", freeze_vit=True, freeze_qformer=True, freeze_llama=True, use_lora=False,
@@ -84,6 +85,8 @@ class Myriad(Blip2Base):
                 raise NotImplementedError("%s=True is not supported by the B200-native Myriad (no 8-bit/CPU/alt paths)" % name)
         if vit_model != "eva_clip_g" or not (freeze_vit and freeze_qformer and freeze_llama) or drop_path_rate:
             raise NotImplementedError("only vit_model=eva_clip_g with frozen ViT / Q-Former / LLaMA and drop_path_rate=0 is supported")
+        if dims is None and os.environ.get("MYRIAD_SYNTHETIC_WEIGHTS", "0") == "1" and os.environ.get("MYRIAD_SYNTHETIC_DIMS", "full") == "mid":
+            dims = syn.mid_dims(lora_r=8 if use_lora else 0)  # reduced depth / width for tests of the config-driven entry points
         self.dims = dims if dims is not None else syn.full_dims(lora_r=8 if use_lora else 0)
         if dims is None:
             self.dims.vit.img = img_size or 224
@@ -295,7 +298,7 @@ class Myriad(Blip2Base):
     @torch.no_grad()
     def generate(self, samples, **generate_kwargs):
         """myriad.py:433-454: stage 1, no bos, greedy search; returns the NEW token ids and the expert maps."""
-        stage = 1
+        stage = self.GENERATE_STAGE
         image, questions, _, maps, refs = self.prepare_sample(samples, stage)
         use = refs if self.k_shot > 0 else maps
         prompts = ["###Human: " + q + " ###Assistant: " for q in questions]

@@ -48,6 +48,9 @@ class _FusedStep(torch.autograd.Function):
     def forward(ctx, model, image, maps, stage, ids_before, ids_after, text_ids, text_mask, keys, *params):
         tr = _trainer_for(model)
         _sync_params_to_trainer(tr, dict(zip(keys, params)))
+        # peft's lora_dropout is live only in train mode (reference: llama_model stays in train() under the runner, myriad.py:171-178)
+        cfg = getattr(model, "lora_config", None) or {}
+        tr.lora_dropout = float(cfg.get("lora_dropout", 0.0)) if model.training else 0.0
         loss = tr.forward_backward(image, maps, stage, ids_before, ids_after, text_ids, text_mask)
         ctx.trainer, ctx.keys, ctx.model = tr, keys, model
         ctx.devices = [p.device for p in params]

@@ -40,6 +40,7 @@ struct Gemm2Params {
   int num_stages, stage_bytes;
   int S, kb_per;       // split-K: S consecutive units share a tile, each covers kb_per k-blocks; partial sums are added in place
   int* flags;          // [tile][rank in pair]: splits of a tile that have written their contribution (ordered => deterministic)
+  int dbg;             // timing ablations (MYR_G2_DBG; results are wrong): 1 no MMAs, 2 no N-side TMA, 4 no A TMA, 8 MMAs with N = 16
   int pf_dist;         // L2 prefetch distance of the weight operand in k-blocks (0 = off)
   uint32_t idesc;
   long long* trace;  // debug (myr_gemm_set_trace): per CTA 6 x %globaltimer ns
@@ -114,7 +115,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       uint16_t mask_rank = 0;
       for (int q = 0; q < p.P; ++q) mask_rank |= (uint16_t)(1u << (2 * q + r));
-      const uint32_t tx_pair = 2u * ((uint32_t)G2_A_BYTES + b_half_bytes);  // bytes landing in both CTAs of a pair per stage
+      const uint32_t tx_pair = 2u * (((p.dbg & 4) ? 0u : (uint32_t)G2_A_BYTES) + ((p.dbg & 2) ? 0u : b_half_bytes));  // bytes landing in both CTAs of a pair per stage
       int stage = 0;
       uint32_t phase = 0;
       pdl_wait();
@@ -143,11 +144,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&empty[stage], phase ^ 1);
           if (r == 0) mbar_arrive_expect_tx(&full[stage], tx_pair);
           uint8_t* sa = smem + stage * p.stage_bytes;
-          if (p.P > 1)
+          if (p.dbg & 4) {
+          } else if (p.P > 1)
             tma_load_2d_pair_multicast(sa + pr * a_slice_rows * (G2_BK * 2), &tmA, &full[stage], kb * G2_BK, a_row0, mask_rank);
           else
             tma_load_2d_pair(sa, &tmA, &full[stage], kb * G2_BK, a_row0);
-          tma_load_2d_pair(sa + G2_A_BYTES, &tmB, &full[stage], kb * G2_BK, b_row0);
+          if (!(p.dbg & 2)) tma_load_2d_pair(sa + G2_A_BYTES, &tmB, &full[stage], kb * G2_BK, b_row0);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -179,7 +181,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int kk = 0; kk < G2_BK / 16; ++kk) {
             const uint64_t da = make_smem_desc(sa + kk * 32, 16, 1024);
             const uint64_t db = make_smem_desc(sb + kk * 32, 16, 1024);
-            tc_mma_f16_pair(d_tmem, da, db, p.idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            if (!(p.dbg & 1)) tc_mma_f16_pair(d_tmem, da, db, p.idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           tc_commit_pair(&empty[stage], mask_all);  // frees this stage in every CTA that multicasts into the pair
           if (++stage == p.num_stages) {
@@ -432,6 +434,8 @@ static void g2_fill(Plan2& pl, int T, int F, int K) {
   pl.stage_bytes = G2_A_BYTES + (pl.BN / 2) * G2_BK * 2;
   int st = G2_SMEM_TILE_BUDGET / pl.stage_bytes;
   pl.num_stages = st > G2_MAX_STAGES ? G2_MAX_STAGES : st;
+  const int f_st = env_int("MYR_G2_STAGES", 0);
+  if (f_st > 0 && f_st < pl.num_stages) pl.num_stages = f_st;
   (void)K;
 }
 
@@ -540,7 +544,8 @@ int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream) {
   p.row_mode = pl.row_mode; p.BN = pl.BN; p.P = pl.P;
   p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.n_ng = pl.n_ng; p.kb_total = ceil_div(a->K, G2_BK); p.n_units = pl.n_units;
   p.num_stages = pl.num_stages; p.stage_bytes = pl.stage_bytes;
-  p.idesc = make_idesc_f16(256, pl.BN, 0, 0);
+  p.dbg = env_int("MYR_G2_DBG", 0);
+  p.idesc = make_idesc_f16(256, (p.dbg & 8) ? 16 : pl.BN, 0, 0);
   p.S = pl.S;
   p.kb_per = ceil_div(p.kb_total, pl.S);
   p.flags = reinterpret_cast<int*>(a->workspace);  // head of the workspace: zero on entry, left at zero (include/myriad_b200.h)

@@ -413,6 +413,44 @@ __global__ void check_finite_kernel(const float* __restrict__ g, long long n, in
   if (bad) atomicExch(found_inf, 1);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// LoRA dropout (peft: lora_dropout = 0.05 on the INPUT of each LoRA branch, myriad.py:171-178). Counter-based mask:
+// element idx of a step's stream keeps its value iff hash(seed, idx) >= p * 2^32 (splitmix64 finaliser), kept values are
+// scaled by 1 / (1 - p). The backward recomputes the same mask from (seed, offset), nothing is stored.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t drop_hash(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__global__ void dropout_fwd_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ out, long long ldo, int rows, int D,
+                                   uint32_t thresh, float keep_scale, unsigned long long seed, unsigned long long offset) {
+  const long long n = (long long)rows * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / D;
+    const int c = (int)(i - t * D);
+    const bool keep = drop_hash(seed, offset + (unsigned long long)i) >= thresh;
+    out[t * ldo + c] = keep ? __float2half_rn(__half2float(x[t * ldx + c]) * keep_scale) : __float2half_rn(0.f);
+  }
+}
+__global__ void dropout_bwd_add_kernel(const float* __restrict__ g, long long ldg, float* __restrict__ acc, long long lda, int rows, int D,
+                                       uint32_t thresh, float keep_scale, unsigned long long seed, unsigned long long offset) {
+  const long long n = (long long)rows * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / D;
+    const int c = (int)(i - t * D);
+    if (drop_hash(seed, offset + (unsigned long long)i) >= thresh) acc[t * lda + c] += g[t * ldg + c] * keep_scale;
+  }
+}
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long n, uint32_t thresh, unsigned long long seed,
+                                    unsigned long long offset) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = drop_hash(seed, offset + (unsigned long long)i) >= thresh ? 1 : 0;
+}
+
 }  // namespace myr
 
 using namespace myr;
@@ -465,6 +503,41 @@ extern "C" int myr_swiglu_bwd(const void* gate_up, int64_t ld_gu, const void* da
   swiglu_bwd_kernel<<<grid_for((long long)T * I, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(gate_up), ld_gu,
                                                                         reinterpret_cast<const __half*>(dact), ld_da,
                                                                         reinterpret_cast<__half*>(dgu), ld_dgu, T, I);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+static inline uint32_t drop_thresh(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
+extern "C" int myr_dropout_fwd(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t rows, int32_t D, float p, uint64_t seed,
+                               uint64_t offset, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(x && out && rows > 0 && D > 0 && p >= 0.f && p < 1.f, "dropout_fwd: bad arguments");
+  dropout_fwd_kernel<<<grid_for((long long)rows * D, 256), 256, 0, stream>>>(reinterpret_cast<const __half*>(x), ldx,
+                                                                             reinterpret_cast<__half*>(out), ldo, rows, D, drop_thresh(p),
+                                                                             1.0f / (1.0f - p), seed, offset);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_dropout_bwd_add(const void* g, int64_t ldg, void* acc, int64_t lda, int32_t rows, int32_t D, float p, uint64_t seed,
+                                   uint64_t offset, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(g && acc && rows > 0 && D > 0 && p >= 0.f && p < 1.f, "dropout_bwd_add: bad arguments");
+  dropout_bwd_add_kernel<<<grid_for((long long)rows * D, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(g), ldg,
+                                                                                 reinterpret_cast<float*>(acc), lda, rows, D, drop_thresh(p),
+                                                                                 1.0f / (1.0f - p), seed, offset);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_dropout_mask(void* out_u8, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(out_u8 && n > 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+  dropout_mask_kernel<<<grid_for(n, 256), 256, 0, stream>>>(reinterpret_cast<unsigned char*>(out_u8), n, drop_thresh(p), seed, offset);
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }

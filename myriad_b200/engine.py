@@ -55,6 +55,9 @@ class MyriadEngine:
         self._prep_qformer(sd)
         self._prep_llama(sd)
         self._decode_graphs = {}
+        # measurement hook (bench.py): when set to a list, every greedy_decode appends (event before the first decode step, event
+        # after the last one, number of decode steps launched), so the decode-step time is taken inside the timed region
+        self.decode_timing = None
         # MYR_MEGA=1: one persistent kernel per decode step (decode_mega.cu) instead of ~230 graph-captured launches. Measured
         # on B200: 4.11 ms/step against 3.70 ms/step for the PDL-chained multi-kernel step, so it is opt-in;
         # tests/test_engine_gpu.py keeps the two paths bit-identical.
@@ -550,6 +553,11 @@ class MyriadEngine:
         l = self.d.llama
         K.greedy_step(logits, st.state, st.scratch, B, l.vocab, st.max_new, st.min_new, l.eos, st.stops, st.n_stops, st.stop_len)
         flags = st.state[:2]
+        ev0 = n_replays = None
+        if self.decode_timing is not None and st.graph is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            n_replays = 0
         while True:
             step, done = flags.tolist()
             if done:
@@ -571,8 +579,14 @@ class MyriadEngine:
                 for _ in range(max(1, min(sync_every, max_new_tokens - step))):
                     st.graph.replay()
                     K.note_graph_replay(st.graph_nodes)
+                    if n_replays is not None:
+                        n_replays += 1
             else:
                 self._decode_step(st)
+        if ev0 is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self.decode_timing.append((ev0, ev1, n_replays))
         n = int(st.state[0].item())
         toks = st.state[4 + 4 * B:].reshape(B, st.max_new)[:, :n]
         return toks.to(torch.int64).cpu()

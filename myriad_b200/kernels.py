@@ -458,6 +458,29 @@ def swiglu_bwd(gu, dact, dgu, T, I):
           "myr_swiglu_bwd")
 
 
+def _u64(v):
+    return ctypes.c_uint64(int(v) & 0xFFFFFFFFFFFFFFFF)
+
+
+def dropout_fwd(x, out, p, seed, offset):
+    rows, D = x.shape
+    check(lib().myr_dropout_fwd(_p(x), _i64(x.stride(0)), _p(out), _i64(out.stride(0)), rows, D, _f32(p), _u64(seed), _u64(offset), _stream()),
+          "myr_dropout_fwd")
+    return out
+
+
+def dropout_bwd_add(g, acc, p, seed, offset):
+    rows, D = g.shape
+    assert g.dtype == torch.float32 and acc.dtype == torch.float32
+    check(lib().myr_dropout_bwd_add(_p(g), _i64(g.stride(0)), _p(acc), _i64(acc.stride(0)), rows, D, _f32(p), _u64(seed), _u64(offset),
+                                    _stream()), "myr_dropout_bwd_add")
+
+
+def dropout_mask(out_u8, p, seed, offset):
+    check(lib().myr_dropout_mask(_p(out_u8), _i64(out_u8.numel()), _f32(p), _u64(seed), _u64(offset), _stream()), "myr_dropout_mask")
+    return out_u8
+
+
 def gelu_fwd(pre, out):
     check(lib().myr_gelu_fwd(_p(pre), _p(out), _i64(pre.numel()), _stream()), "myr_gelu_fwd")
 

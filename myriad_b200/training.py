@@ -35,7 +35,11 @@ class MyriadTrainer(MyriadEngine):
     FUSED_LLAMA = False  # plain weight layout: the backward needs the pre-activation gate/up values and xa = x A^T
 
     def __init__(self, sd, dims, device="cuda:0", max_batch=8, max_seq=512, loss_scale=1024.0, lr=1e-4, betas=(0.9, 0.999),
-                 eps=1e-8, weight_decay=0.05):
+                 eps=1e-8, weight_decay=0.05, lora_dropout=0.0, dropout_seed=0):
+        # peft's lora_dropout (0.05 in the reference's LoraConfig, myriad.py:171-178): the only stochastic op of the training hot
+        # path. 0.0 = off (parity runs against the oracle use a shared mask or no dropout). The mask stream is keyed by
+        # (dropout_seed, forward count, layer, branch), see _lora_drop_offset.
+        self.lora_dropout, self.dropout_seed, self.fwd_count = float(lora_dropout), int(dropout_seed), 0
         self._sd_for_flat = sd
         super().__init__(sd, dims, device, max_batch, max_seq)
         self.loss_scale = float(loss_scale)
@@ -508,10 +512,19 @@ class MyriadTrainer(MyriadEngine):
             Sv.x1 = self._e(T, D)
             K.norm(h, L.n1, None, l.eps, rms=True, out16=Sv.x1)
             Sv.qkv = K.gemm(Sv.x1, L.wqkv)
-            Sv.xa = None
+            Sv.xa = Sv.xd = None
             if L.lora is not None:
                 r = self.d.lora_r
-                Sv.xa = K.gemm(Sv.x1, L.lora.a)
+                if self.lora_dropout > 0.0:
+                    # peft: each LoRA module drops its own copy of the input: B_q(A_q(drop_q(x))) and B_v(A_v(drop_v(x)))
+                    Sv.xa = self._e(T, 2 * r)
+                    Sv.xd = []
+                    for j in range(2):
+                        xd = K.dropout_fwd(Sv.x1, self._e(T, D), self.lora_dropout, self.dropout_seed, self._lora_drop_offset(li, j, T * D))
+                        K.gemm(xd, L.lora.a[j * r:(j + 1) * r], out=Sv.xa[:, j * r:], T=T, F=r, K=D, ldo=2 * r)
+                        Sv.xd.append(xd)
+                else:
+                    Sv.xa = K.gemm(Sv.x1, L.lora.a)
                 K.gemm(Sv.xa[:, :r], L.lora.bq, res=Sv.qkv[:, :D], out=Sv.qkv[:, :D], T=T, K=r, alpha=L.lora.scale)
                 K.gemm(Sv.xa[:, r:], L.lora.bv, res=Sv.qkv[:, 2 * D:], out=Sv.qkv[:, 2 * D:], T=T, K=r, alpha=L.lora.scale)
             K.rope_cache(Sv.qkv, B, S, H, dh, tp.pos, self.llw.cos, self.llw.sin, kc, vc)
@@ -528,6 +541,10 @@ class MyriadTrainer(MyriadEngine):
         x16 = self._e(T, D)
         K.norm(h, self.llw.norm, None, l.eps, rms=True, out16=x16)
         return K.gemm(x16, self.llw.lm_head, out_dtype=F32)  # [T, V] fp32 (modeling_llama.py:690)
+
+    def _lora_drop_offset(self, layer, branch, n):
+        """Start of the mask stream of (this forward, layer, branch q / v): streams never overlap within a run."""
+        return ((self.fwd_count * self.d.llama.layers + layer) * 2 + branch) * n
 
     def _llama_train_bwd(self, dlogits16, tp, B):
         """dlogits16 fp16 [T, V] (already multiplied by loss_scale) -> fp32 [T, D] gradient of inputs_embeds; LoRA A/B
@@ -569,9 +586,17 @@ class MyriadTrainer(MyriadEngine):
                     K.gemm(dy, b16, out=d_xa[:, j * r:], w_mn_major=True, T=T, F=r, K=D, ldx=3 * D, ldo=2 * r, alpha=s)
                 # dA[2r, D] = sum_t d_xa[t, :]^T x1[t, :]   (A_q and A_v are adjacent in the flat buffer)
                 o = self.segments[p + "q_proj.lora_A.default.weight"][0]
-                K.gemm(d_xa, Sv.x1, out=self.flat_grads[o:o + 2 * r * D].view(2 * r, D), x_mn_major=True, w_mn_major=True, T=2 * r, F=D,
-                       K=T, bn_hint=64, alpha=inv_scale)
-                K.gemm(d_xa, L.lora.a, w_mn_major=True, T=T, F=D, K=2 * r, res=d_x1, out=d_x1)
+                if Sv.xd is None:
+                    K.gemm(d_xa, Sv.x1, out=self.flat_grads[o:o + 2 * r * D].view(2 * r, D), x_mn_major=True, w_mn_major=True, T=2 * r,
+                           F=D, K=T, bn_hint=64, alpha=inv_scale)
+                    K.gemm(d_xa, L.lora.a, w_mn_major=True, T=T, F=D, K=2 * r, res=d_x1, out=d_x1)
+                else:  # with dropout: A sees the dropped inputs, and the input gradient passes through the same mask
+                    g_in = self._e(T, D, dtype=F32)
+                    for j in range(2):
+                        K.gemm(d_xa[:, j * r:], Sv.xd[j], out=self.flat_grads[o + j * r * D:o + (j + 1) * r * D].view(r, D), x_mn_major=True,
+                               w_mn_major=True, T=r, F=D, K=T, ldx=2 * r, bn_hint=64, alpha=inv_scale)
+                        K.gemm(d_xa[:, j * r:], L.lora.a[j * r:(j + 1) * r], out=g_in, w_mn_major=True, T=T, F=D, K=r, ldx=2 * r)
+                        K.dropout_bwd_add(g_in, d_x1, self.lora_dropout, self.dropout_seed, self._lora_drop_offset(li, j, T * D))
             dh32, dh16 = self._norm_bwd(Sv.h_in, d_x1, L.n1, l.eps, rms=True, add=dmid32, want16=li > 0)
         return dh32
 
@@ -585,6 +610,7 @@ class MyriadTrainer(MyriadEngine):
         B, D = image.shape[0], l.hidden
         inv_scale = 1.0 / self.loss_scale
         K.memset_zero(self.flat_grads)
+        self.fwd_count += 1
         tp = self._tape = _Obj()
         try:
             emb = self.build_inputs_embeds(image, maps, stage, ids_before, ids_after, with_bos=True, text_ids=text_ids)

@@ -204,12 +204,12 @@ def rms_norm(x, w, eps):
     return w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
 
 
-def rope_tables(dh, max_pos, base=10000.0):
-    """LlamaRotaryEmbedding.__init__ :78-91 (freqs duplicated, not interleaved)."""
-    inv = 1.0 / (base ** (torch.arange(0, dh, 2).float() / dh))
-    fr = torch.outer(torch.arange(max_pos).float(), inv)
+def rope_tables(dh, max_pos, base=10000.0, device="cpu", dtype=torch.float32):
+    """LlamaRotaryEmbedding.__init__ :78-91 (freqs duplicated, not interleaved); cached tables are cast to x.dtype (:103-106)."""
+    inv = 1.0 / (base ** (torch.arange(0, dh, 2, device=device).float() / dh))
+    fr = torch.outer(torch.arange(max_pos, device=device).float(), inv)
     emb = torch.cat([fr, fr], -1)
-    return emb.cos(), emb.sin()
+    return emb.cos().to(dtype), emb.sin().to(dtype)
 
 
 def apply_rope(x, cos, sin, position_ids):
@@ -221,11 +221,17 @@ def apply_rope(x, cos, sin, position_ids):
     return x * c + rot * s
 
 
+LORA_DROP = None  # tests only: {(layer, "q_proj" | "v_proj"): keep-mask [T, D] already scaled by 1 / (1 - p)} shared with the device path
+
+
 def _lora(sd, i, name, x, d):
     """peft LoRA (third-party, unpinned; restated from its published definition with the config at
-    myriad.py:171-178): y += (alpha / r) * B(A(x)); dropout is identity in eval / parity runs."""
+    myriad.py:171-178): y += (alpha / r) * B(A(dropout(x))); dropout is identity in eval / parity runs unless a shared mask is
+    supplied through LORA_DROP (peft: every LoRA module owns its nn.Dropout(lora_dropout) applied to its input)."""
     if d.lora_r <= 0:
         return 0.0
+    if LORA_DROP is not None:
+        x = x * LORA_DROP[(i, name)].reshape(x.shape)
     p = "llama_model.base_model.model.model.layers.%d.self_attn.%s." % (i, name)
     return (d.lora_alpha / d.lora_r) * linear(linear(x, sd[p + "lora_A.default.weight"]), sd[p + "lora_B.default.weight"])
 
@@ -236,7 +242,7 @@ def llama_layers(sd, h, attn_bias, position_ids, d: MyriadDims, past=None, p="ll
     l = d.llama
     B, S, _ = h.shape
     H, dh = l.heads, l.head_dim
-    cos, sin = rope_tables(dh, l.max_pos)
+    cos, sin = rope_tables(dh, l.max_pos, device=h.device, dtype=h.dtype)
     new_past = []
     for i in range(l.layers):
         lp = p + "layers.%d." % i
@@ -251,7 +257,7 @@ def llama_layers(sd, h, attn_bias, position_ids, d: MyriadDims, past=None, p="ll
             v = torch.cat([past[i][1], v], 2)
         new_past.append((k, v))
         s = (q @ k.transpose(2, 3)) / math.sqrt(dh) + attn_bias
-        s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min))
+        s = torch.max(s, torch.tensor(torch.finfo(s.dtype).min, device=s.device, dtype=s.dtype))
         a = (softmax_lastdim(s) @ v).transpose(1, 2).reshape(B, S, l.hidden)
         h = h + linear(a, sd[lp + "self_attn.o_proj.weight"])
         x = rms_norm(h, sd[lp + "post_attention_layernorm.weight"], l.eps)
@@ -260,15 +266,16 @@ def llama_layers(sd, h, attn_bias, position_ids, d: MyriadDims, past=None, p="ll
     return rms_norm(h, sd[p + "norm.weight"], l.eps), new_past
 
 
-def causal_bias(attention_mask, q_len, past_len=0):
+def causal_bias(attention_mask, q_len, past_len=0, dtype=torch.float32):
     """_make_causal_mask + _expand_mask + _prepare_decoder_attention_mask :25-54,442-463.
     attention_mask: [B, past_len + q_len] of 0/1."""
-    neg = torch.finfo(torch.float32).min
+    neg = torch.finfo(dtype).min
+    dev = attention_mask.device
     B, kv = attention_mask.shape
-    bias = torch.zeros(B, 1, q_len, kv)
+    bias = torch.zeros(B, 1, q_len, kv, device=dev, dtype=dtype)
     if q_len > 1:
-        qi = torch.arange(q_len)[:, None] + past_len
-        ki = torch.arange(kv)[None, :]
+        qi = torch.arange(q_len, device=dev)[:, None] + past_len
+        ki = torch.arange(kv, device=dev)[None, :]
         bias = bias.masked_fill((ki > qi)[None, None], neg)
     pad = (attention_mask == 0)[:, None, None, :].expand(B, 1, q_len, kv)
     bias = bias + torch.zeros_like(bias).masked_fill(pad, neg)
@@ -280,8 +287,8 @@ def llama_logits(sd, inputs_embeds, attention_mask, d, position_ids=None, past=N
     B, S, _ = inputs_embeds.shape
     past_len = 0 if past is None else past[0][0].shape[2]
     if position_ids is None:
-        position_ids = torch.arange(past_len, past_len + S)[None].expand(B, -1)
-    h, new_past = llama_layers(sd, inputs_embeds, causal_bias(attention_mask, S, past_len), position_ids, d, past)
+        position_ids = torch.arange(past_len, past_len + S, device=inputs_embeds.device)[None].expand(B, -1)
+    h, new_past = llama_layers(sd, inputs_embeds, causal_bias(attention_mask, S, past_len, dtype=inputs_embeds.dtype), position_ids, d, past)
     return linear(h, sd["llama_model.lm_head.weight"]), new_past
 
 
@@ -355,9 +362,10 @@ def greedy_generate(sd, inputs_embeds, d: MyriadDims, max_new_tokens=90, stop_se
     pad = eos, StoppingCriteriaSub conversation.py:96-107 (row 0 only). Returns NEW tokens only."""
     l = d.llama
     B, S, _ = inputs_embeds.shape
-    mask = torch.ones(B, S, dtype=torch.long)
+    dev = inputs_embeds.device
+    mask = torch.ones(B, S, dtype=torch.long, device=dev)
     logits, past = llama_logits(sd, inputs_embeds, mask, d)
-    unfinished = torch.ones(B, dtype=torch.long)
+    unfinished = torch.ones(B, dtype=torch.long, device=dev)
     out, margins = [], []
     for step in range(max_new_tokens):
         nl = logits[:, -1].clone()
@@ -373,7 +381,7 @@ def greedy_generate(sd, inputs_embeds, d: MyriadDims, max_new_tokens=90, stop_se
         stop = any(len(row0) >= len(s) and tuple(row0[-len(s):]) == tuple(s) for s in stop_seqs)
         if stop or int(unfinished.max()) == 0 or step == max_new_tokens - 1:
             break
-        mask = torch.cat([mask, torch.ones(B, 1, dtype=torch.long)], 1)
+        mask = torch.cat([mask, torch.ones(B, 1, dtype=torch.long, device=dev)], 1)
         pos = (mask.cumsum(-1) - 1)[:, -1:]
         logits, past = llama_logits(sd, embed_tokens(sd, nxt[:, None]), mask, d, position_ids=pos, past=past)
     toks = torch.stack(out, 1)

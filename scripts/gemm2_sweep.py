@@ -37,6 +37,10 @@ GROUPS = {
     "pf": [(sh, 0, bn, 1, 1, {"MYR_G2_PF": str(pf)}) for sh, bn in (("ll_gu", 176), ("ll_qkv", 176), ("vit_fc1", 176), ("big_gu", 256))
            for pf in (0, 4, 8, 16)],
     "prof": [("vit_qkv", 0, 208, 1, 1), ("ll_o", 0, 176, 1, 1), ("vit_fc1", 0, 208, 1, 1)],
+    "lat": [(sh, 0, bn, 1, 1, {"MYR_G2_STAGES": str(st), "NW": str(nw)}) for sh, bn in (("vit_qkv", 208), ("ll_gu", 176), ("ll_qkv", 176))
+            for st, nw in ((6, 8), (4, 8), (3, 8), (2, 8), (6, 1))] +
+           [("ll_gu", 0, bn, 1, 1, {"NW": "2"}) for bn in (96, 128, 176, 256)] + [("big_gu", 0, bn, 1, 1, {"NW": "2"}) for bn in (128, 192, 256)],
+    "abl": [("ll_gu", 0, bn, 1, 1, {"NW": "2", "MYR_G2_DBG": str(d)}) for bn in (176,) for d in (0, 1, 2, 4, 6, 8, 3, 5)],
     "m1": [("vit_fc1", 1, 256, 1, 1), ("ll_gu", 1, 256, 1, 1), ("big_gu", 1, 256, 1, 1), ("big_down", 1, 256, 1, 1)],
 }
 
@@ -60,6 +64,9 @@ def run_group(name):
             else:
                 os.environ.pop(k, None)
         nw = 8 if T * F < 5e7 else 2  # rotate over more weight bytes than the 126 MB L2 holds
+        nw = int(extra.get("NW", nw))
+        os.environ["MYR_G2_STAGES"] = extra.get("MYR_G2_STAGES", "0")
+        os.environ["MYR_G2_DBG"] = extra.get("MYR_G2_DBG", "0")
         x = torch.randn(T, Kd, device=dev).half()
         ws = [(torch.randn(F, Kd, device=dev) / Kd ** 0.5).half() for _ in range(nw)]
         bias = torch.randn(F, device=dev).half() if kw.get("bias") else None

@@ -340,3 +340,49 @@ def test_checkpoint_resume_and_lr_schedule(tmp_path):
     moved = max(rel(pa[k], sd[k]) for k in pa)
     print("resume: worst parameter difference after the resumed step %.2e (parameters moved %.2e from init)" % (worst, moved))
     assert worst < 1e-5 and moved > 1e-4
+
+
+def test_lora_dropout_shared_mask_vs_oracle(O):
+    """peft's lora_dropout = 0.05 (myriad.py:175), the only stochastic op of the training hot path: the device draws
+    counter-based masks (one per layer and per LoRA branch, regenerated in the backward); the SAME masks, exported with
+    myr_dropout_mask, are handed to the oracle's autograd. Loss and LoRA A / B gradients must agree, and must differ from
+    the dropout-free run (i.e. the mask really is applied)."""
+    from myriad_b200 import kernels as K
+    from myriad_b200.training import MyriadTrainer
+    p_drop = 0.25  # larger than the reference's 0.05 so a missing / misplaced mask cannot hide inside the tolerance
+    d = syn.mid_dims(lora_r=8)
+    sd = syn.make_state_dict(d, 2)
+    image, maps = syn.make_inputs(2, seed=77)
+    ids_b, ids_a = syn.make_prompt_ids(d.llama.vocab)
+    gen = torch.Generator().manual_seed(3)
+    text = torch.randint(3, d.llama.vocab, (2, 8), generator=gen)
+    tmask = torch.ones(2, 8, dtype=torch.long)
+    tr = MyriadTrainer(sd, d, device="cuda:0", max_batch=2, max_seq=256, lora_dropout=p_drop, dropout_seed=1234)
+    loss = tr.forward_backward(image.cuda(), maps.cuda(), 1, ids_b, ids_a, text, tmask)
+    grads = tr.export_grads()
+    L = 1 + 6 + tr.num_image_tokens(1) + 26 + 8
+    T, D = 2 * L, d.llama.hidden
+    masks = {}
+    for li in range(d.llama.layers):
+        for j, name in enumerate(("q_proj", "v_proj")):
+            m = torch.empty(T * D, dtype=torch.uint8, device="cuda:0")
+            K.dropout_mask(m, p_drop, 1234, tr._lora_drop_offset(li, j, T * D))
+            masks[(li, name)] = m.cpu().float().reshape(2, L, D) / (1.0 - p_drop)
+    keep = torch.stack([m for m in masks.values()]).ne(0).float().mean().item()
+    assert abs(keep - (1.0 - p_drop)) < 0.01, "keep rate %.4f" % keep
+    O.LORA_DROP = masks
+    try:
+        oloss, ograds = O.train_grads(sd, d, image, maps, 1, ids_b, ids_a, text, tmask, conv_fp16=True)
+    finally:
+        O.LORA_DROP = None
+    oloss0, ograds0 = O.train_grads(sd, d, image, maps, 1, ids_b, ids_a, text, tmask, conv_fp16=True)
+    lora = [k for k in ograds if ".lora_" in k]
+    worst = max(rel(grads[k], ograds[k]) for k in lora)
+    apart = max(rel(ograds0[k], ograds[k]) for k in lora)
+    print("LoRA dropout p=%.2f: loss %.5f (oracle with the same masks %.5f, without %.5f); worst LoRA grad rel err %.2e; "
+          "dropout moves the oracle's own LoRA grads by %.2e" % (p_drop, loss.item(), oloss.item(), oloss0.item(), worst, apart))
+    assert abs(loss.item() - oloss.item()) < 2e-2
+    assert worst < TOL_GRAD and apart > 5 * worst
+    # a second forward draws fresh masks
+    loss2 = tr.forward_backward(image.cuda(), maps.cuda(), 1, ids_b, ids_a, text, tmask)
+    assert loss2.item() != loss.item()
