@@ -477,6 +477,79 @@ def tensor_context(eng, dims, dev, peaks):
                                 "avg_launch_us": ms2 * 1e3}}
 
 
+def run_sweep(args):
+    """BASELINE.json configs[4]: batch {1,4,16,32} x LLM sequence {256,1024,2048}: images/s (forward + greedy decode of NEW_TOKENS
+    tokens) and prompt tokens/s, with the decode step's fraction of the HBM roofline, per GPU and whole-job (replicas). One JSON
+    line per point; rank 0 also writes them to --sweep-out."""
+    import torch
+    import torch.distributed as dist
+
+    from myriad_b200 import synthetic as syn
+    from myriad_b200.engine import MyriadEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dims = syn.full_dims(lora_r=8)
+    peaks = _peaks()
+    batches = [int(x) for x in args.sweep_batches.split(",")]
+    seqs = [int(x) for x in args.sweep_seqs.split(",")]
+    eng = MyriadEngine(syn.LazyStateDict(dims, seed=0, device=dev), dims, device=dev, max_batch=max(batches), max_seq=max(seqs) + NEW_TOKENS)
+    l = dims.llama
+    stops = ((835,), (2277, 29937))
+    n_img = eng.num_image_tokens(1)
+    wq = eng.llw.layers[0].wqkv.shape[0]
+    w_step = l.layers * 2 * (wq * l.hidden + l.hidden * l.hidden + 3 * l.inter * l.hidden) + 2 * l.vocab * l.hidden
+    out = []
+    for B in batches:
+        image, maps = syn.make_inputs(B, seed=1234 + rank, device="cpu")
+        image_d, maps_d = image.to(dev), maps.to(dev)
+        for S in seqs:
+            ids_b, ids_a = syn.make_prompt_ids(l.vocab, n_before=6, n_after=S - 6 - n_img)
+
+            def step():
+                return eng.generate(image_d, maps_d, ids_b, ids_a, max_new_tokens=NEW_TOKENS, stop_seqs=stops)
+
+            for _ in range(max(1, min(args.warmup, 2))):
+                step()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            eng.decode_timing = []
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = max(1, min(args.steps, 3))
+            e0.record()
+            for _ in range(n):
+                toks = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            ev, eng.decode_timing = eng.decode_timing, None
+            dec_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / max(1, sum(c for _, _, c in ev))
+            kv = 2 * l.layers * B * (S + NEW_TOKENS // 2) * l.hidden * 2
+            frac_step = (w_step + kv) / (dec_ms / 1e3) / 1e9 / peaks["hbm"] if dec_ms > 0 else None
+            rec = {"sweep": True, "batch_per_gpu": B, "seq_len": S, "n_gpus": world, "new_tokens": int(toks.shape[1]), "ms_per_step": ms,
+                   "images_per_s": world * B / (ms / 1e3), "prompt_tokens_per_s": world * B * S / (ms / 1e3),
+                   "new_tokens_per_s": world * B * int(toks.shape[1]) / (ms / 1e3), "decode_step_ms": dec_ms,
+                   "decode_frac_of_hbm_roofline": frac_step, "hbm_peak_gbs": peaks["hbm"]}
+            out.append(rec)
+            if rank == 0:
+                print(json.dumps(rec), flush=True)
+    if rank == 0 and args.sweep_out:
+        with open(args.sweep_out, "w") as fh:
+            json.dump(out, fh, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """Reference arm for this tier: the reference's own CPU implementation of the path, i.e. the fp32 oracle port
     (the reference module files cannot travel to the GPU box), with all host threads, on a bounded sample per step."""
@@ -516,10 +589,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train tokens/s)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager fp16 GPU baseline of the same workload")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: batch x sequence throughput sweep instead of the headline line")
+    ap.add_argument("--sweep-batches", default="1,4,16,32")
+    ap.add_argument("--sweep-seqs", default="256,1024,2048")
+    ap.add_argument("--sweep-out", default="")
     ap.add_argument("--profile", action="store_true", help="minimal run for ncu (numbers printed under a profiler are not bench values)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.sweep:
+        run_sweep(args)
     else:
         run_ours(args)
 

@@ -131,6 +131,9 @@ typedef struct {
   int32_t bn_hint;         /* keys per tile (multiple of 32), 0 = auto */
 } myr_attn_args;
 int myr_attention_fwd(const myr_attn_args* args, void* stream);
+/* profiling aid: attention launches after this call write %globaltimer stamps of their CTA (0,0,0) at buf (256 x int64:
+ * per KV tile scores seen / probabilities handed over / P.V issued / iteration end); NULL switches it off */
+void myr_attn_set_trace(void* buf);
 
 /* ---- LayerNorm / RMSNorm (+ fused LoraAdaptorV2) ----------------------------------------------------
  * y = norm(x [+ W2 (W1 x)]) * gamma (+ beta); statistics in fp32. Replaces blip2.py:119-125 (ln_vision),

@@ -1,6 +1,8 @@
-"""Blip2Base with the reference's interface (minigpt4/models/blip2.py:32-125): `maybe_autocast`, `init_tokenizer`,
-`init_vision_encoder`, `init_Qformer`, `load_from_pretrained`, `LayerNorm`, `disabled_train`. In this implementation
-the vision encoder and Q-Former are not nn.Modules but weight sets executed by myriad_b200.engine.MyriadEngine."""
+"""Blip2Base with the part of the reference's interface (minigpt4/models/blip2.py:32-125) that the Myriad callers use:
+`init_tokenizer`, `maybe_autocast`, plus the module-level `LayerNorm` and `disabled_train`. The reference's
+`init_vision_encoder` / `init_Qformer` / `load_from_pretrained` build nn.Modules; here the vision encoder and the Q-Former
+are weight sets executed by myriad_b200.engine.MyriadEngine and are loaded by minigpt4/models/checkpoints.py, so those three
+methods do not exist."""
 import contextlib
 import os
 

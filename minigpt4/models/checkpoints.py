@@ -10,10 +10,6 @@ import os
 import torch
 
 
-class _Lazy(dict):
-    """key -> tensor, with tensors of sharded files loaded on first access and cached per file."""
-
-
 def _need(path, what):
     if not path or not os.path.exists(path):
         raise FileNotFoundError(
@@ -31,6 +27,8 @@ def load_reference_checkpoints(dims, llama_model, q_former_model):
             vit_path = cand
             break
     vit = torch.load(_need(vit_path, "EVA-ViT-g weights (eva_vit_g.pth)"), map_location="cpu")
+    if isinstance(vit, dict) and "model" in vit and "cls_token" not in vit:
+        vit = vit["model"]
     for k, v in vit.items():
         sd["visual_encoder." + k] = v
     qf = torch.load(_need(q_former_model, "BLIP-2 Q-Former checkpoint (q_former_model)"), map_location="cpu")["model"]

@@ -25,6 +25,7 @@ def _trainer_for(model):
         dev = torch.device("cuda", torch.cuda.current_device())
         tr = MyriadTrainer(model._Merged(model._frozen, model.trainable_state()), model.dims, device=dev,
                            max_batch=8, max_seq=512)
+        tr.overlap_allreduce = False  # under the runner the whole flat buffer is averaged once, in _FusedStep.backward
         model._trainer = tr
     return tr
 

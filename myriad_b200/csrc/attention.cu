@@ -258,6 +258,11 @@ static uint32_t pow2_cols(int c) {
 
 }  // namespace myr
 
+namespace myr {
+bool attn2_enabled();  // attention2.cu: the warp-specialised kernel (default); MYR_ATTN2=0 or a bn_hint select this file's kernel
+int attn2_launch(const myr_attn_args* a, cudaStream_t stream);
+}
+
 using namespace myr;
 
 extern "C" int myr_attention_fwd(const myr_attn_args* a, void* stream_) {
@@ -269,6 +274,7 @@ extern "C" int myr_attention_fwd(const myr_attn_args* a, void* stream_) {
   MYR_CHECK_ARG(a->q && a->k && a->v && a->out, "attention: null pointer");
   MYR_CHECK_ARG(a->bn_hint == 0 || (a->bn_hint % 32 == 0 && a->bn_hint >= 32 && a->bn_hint <= 256),
                 "attention: bn_hint %d must be a multiple of 32 in [32,256]", a->bn_hint);
+  if (attn2_enabled() && a->bn_hint == 0) return attn2_launch(a, stream);
 
   AttnKernelParams p;
   p.Sq = a->Sq; p.Skv = a->Skv; p.dh = a->dh;

@@ -613,7 +613,7 @@ extern "C" size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K) {
 int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter);  // gemv.cu
 namespace myr {
 bool gemm2_eligible(const myr_gemm_args* a, int nbatch);  // gemm2.cu: CTA-pair kernel for the tensor-bound shapes
-int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream);
+int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled);
 }
 
 static int g_gemv = -1;  // < 0: not read from the environment yet
@@ -670,7 +670,11 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
     return MYR_ERR_UNSUPPORTED;
   }
 
-  if (gemm2_eligible(a, nbatch)) return gemm2_launch(a, stream);
+  if (gemm2_eligible(a, nbatch)) {
+    int handled = 0;
+    const int rc = gemm2_launch(a, stream, &handled);
+    if (handled || rc != MYR_OK) return rc;
+  }
 
   size_t ws_floats = 0;
   int* counters = nullptr;

@@ -28,9 +28,11 @@ constexpr int G2_BK = 64;                         // halfs per k-block = one 128
 constexpr int G2_A_ROWS = 128;                    // rows of A per CTA (UMMA M = 256 over the pair)
 constexpr int G2_A_BYTES = G2_A_ROWS * G2_BK * 2;  // 16 KiB
 constexpr int G2_MAX_STAGES = 8;
-constexpr int G2_THREADS = 64 + EPI_THREADS;
+constexpr int G2_EPI_WARPS = 16;  // 4 per TMEM lane quarter: the epilogue is latency-bound (global loads / stores, erf), more warps hide it
+constexpr int G2_EPI_THREADS = 32 * G2_EPI_WARPS;
+constexpr int G2_THREADS = 64 + G2_EPI_THREADS;
 constexpr int G2_SMEM_TILE_BUDGET = 192 * 1024;
-constexpr int G2_SWIGLU_STAGE_BYTES = 2 * 2 * 16 * 64 * 4;  // lanes = features SwiGLU: [hsel][buffer][16 tokens][64 up rows] fp32
+constexpr int G2_SWIGLU_STAGE_BYTES = 4 * 2 * 16 * 64 * 4;  // lanes = features SwiGLU: [csel][buffer][16 tokens][64 up rows] fp32
 
 struct Gemm2Params {
   int T, F, K;
@@ -90,7 +92,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 2 * N_EPI_WARPS);
+      mbar_init(&tempty[s], 2 * G2_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -142,6 +144,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           mbar_wait(&empty[stage], phase ^ 1);
+          if ((p.dbg & 16) && p.trace && blockIdx.x < 2 && u == cluster_id && kb < 64) p.trace[888 + (blockIdx.x ? 128 : 0) + kb] = gtime_ns();
           if (r == 0) mbar_arrive_expect_tx(&full[stage], tx_pair);
           uint8_t* sa = smem + stage * p.stage_bytes;
           if (p.dbg & 4) {
@@ -175,6 +178,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if ((p.dbg & 16) && p.trace && blockIdx.x == 0 && u == cluster_id && kb < 64) p.trace[888 + 64 + kb] = gtime_ns();
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
           const uint32_t sb = sa + G2_A_BYTES;
 #pragma unroll
@@ -198,9 +202,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // ------------------------------ epilogue (warps 2..9 of both CTAs) ------------------------------
+    // ------------------------------ epilogue (warps 2..17 of both CTAs) ------------------------------
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int hsel = (warp - 2) >> 2;  // which half of the column chunks this warp handles
+    const int csel = (warp - 2) >> 2;  // which quarter of the column chunks this warp handles (chunks csel, csel + 4, ...)
     const int lrow = q * 32 + lane;    // TMEM lane == row of this CTA's half of the A tile
     const bool swiglu = p.ep.act == MYR_ACT_SWIGLU;
     const int nchunks = p.BN / 16;
@@ -213,6 +217,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       g2_unit(p, u, mt, ng, ks);
       const int m0 = mt * 256 + r * G2_A_ROWS;
       const int n0 = (ng * p.P + pr) * p.BN;
+      // fp32 residual epilogue (o_proj / down_proj / ViT proj / fc2): this warp's first two chunks of residual values are
+      // requested BEFORE the accumulator is awaited, so their L2 latency hides behind the unit's MMAs
+      float pre[2][16];
+      bool pre_ok = false;
+      if (!p.row_mode && !swiglu && ks == 0 && p.ep.res != nullptr && p.ep.res_dtype == MYR_F32 && p.ep.out_dtype == MYR_F32 &&
+          p.ep.act == MYR_ACT_NONE && !p.ep.round_acc && p.ep.scale_cols == 0 && p.ep.group_rows == 0 && m0 + lrow < p.F) {
+        pre_ok = true;
+        const float* rbase = reinterpret_cast<const float*>(p.ep.res) + (m0 + lrow);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int t0 = n0 + (csel + 4 * h2) * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pre[h2][j] = (t0 + j < p.T && (csel + 4 * h2) * 16 + j < p.BN) ? __ldcg(rbase + (long long)(t0 + j) * p.ep.ldr) : 0.f;
+        }
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       if (p.trace && threadIdx.x == 64) p.trace[blockIdx.x * 6 + 3] = gtime_ns();  // accumulator of the (last) unit ready
@@ -222,7 +241,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool t_ok = t < p.T;
         const long long obase = t_ok ? out_row_offset(p.ep, t) : 0;
         if (!swiglu) {
-          for (int ch = hsel; ch < nchunks; ch += 2) {
+          for (int ch = csel; ch < nchunks; ch += 4) {
             const int f0 = n0 + ch * 16;
             if (f0 >= p.F) break;
             uint32_t rr[16];
@@ -238,7 +257,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else {
           // weight rows are interleaved in blocks of 64: [gate 0..63 | up 0..63 | gate 64..127 | ...]; BN % 128 == 0
           const int units = p.BN / 32;
-          for (int uu = hsel; uu < units; uu += 2) {
+          for (int uu = csel; uu < units; uu += 4) {
             const int blk = uu >> 2, cg = uu & 3;
             const int gcol = blk * 128 + cg * 16;
             if (n0 + gcol >= p.F) break;
@@ -268,19 +287,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int nch = cols > 0 ? (cols + 15) >> 4 : 0;
         const bool plain = !ep.round_acc && ep.scale_cols == 0 && ep.group_rows == 0;
         const bool fast16 = plain && ep.out_dtype == MYR_F16 && ep.res == nullptr && ep.alpha == 1.0f && ep.act != MYR_ACT_SWIGLU;
-        const bool fast32 = plain && ep.out_dtype == MYR_F32 && ep.res != nullptr && ep.res_dtype == MYR_F32 && ep.act == MYR_ACT_NONE;
+        const bool fast32 = plain && ep.out_dtype == MYR_F32 && (ep.res == nullptr || ep.res_dtype == MYR_F32) && ep.act == MYR_ACT_NONE;
+        const bool has_res = ep.res != nullptr || ks > 0;
         const int tile_flag = ((mt * p.n_nt + ng * p.P + pr) << 1) + r;
         if (p.S > 1 && ks > 0) {  // ordered in-place accumulation: wait until the splits below this one have landed
           if (threadIdx.x == 64) {
             while (ld_acquire(p.flags + tile_flag) != ks) __nanosleep(64);
           }
-          g2_bar_sync(1, EPI_THREADS);
+          g2_bar_sync(1, G2_EPI_THREADS);
         }
-        auto do_chunk = [&](const uint32_t (&rr)[16], int ch) {
+        auto do_chunk = [&](const uint32_t (&rr)[16], int ch, const float* have) {
           const int t0 = n0 + ch * 16;
           const int nc = min(16, p.T - t0);
           if (!f_ok) return;
-          if (fast32) {
+          if (fast32 && have != nullptr) {
+            float* op = reinterpret_cast<float*>(ep.out) + (long long)t0 * ep.ldo + f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nc) op[j * ep.ldo] = (__uint_as_float(rr[j]) + bias_f) * ep.alpha + have[j];
+          } else if (fast32) {
             // out = (acc + bias) * alpha + res: all residual loads are issued before the first store (res may alias out)
             const float* rp = (ks == 0 ? reinterpret_cast<const float*>(ep.res) + (long long)t0 * ep.ldr
                                        : reinterpret_cast<const float*>(ep.out) + (long long)t0 * ep.ldo) + f;
@@ -288,7 +313,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             float* op = reinterpret_cast<float*>(ep.out) + (long long)t0 * ep.ldo + f;
             float rv[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rv[j] = (j < nc) ? __ldcg(rp + j * ldr) : 0.f;
+            for (int j = 0; j < 16; ++j) rv[j] = (has_res && j < nc) ? __ldcg(rp + j * ldr) : 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (j < nc) op[j * ep.ldo] = (__uint_as_float(rr[j]) + bias_f) * ep.alpha + rv[j];
@@ -320,18 +345,24 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         };
         // two TMEM loads in flight per wait: 32 independent columns of epilogue work behind every tcgen05.wait::ld
-        for (int ch = hsel; ch < nch; ch += 4) {
+        for (int ch = csel; ch < nch; ch += 8) {
           uint32_t ra[16], rb[16];
-          const bool two = ch + 2 < nch;
+          const bool two = ch + 4 < nch;
           tmem_ld16(taddr + ch * 16, ra);
-          if (two) tmem_ld16(taddr + (ch + 2) * 16, rb);
+          if (two) tmem_ld16(taddr + (ch + 4) * 16, rb);
           tmem_ld_wait();
-          do_chunk(ra, ch);
-          if (two) do_chunk(rb, ch + 2);
+          const bool first = pre_ok && ch == csel;
+          if (first) {
+            do_chunk(ra, ch, pre[0]);
+            if (two) do_chunk(rb, ch + 4, pre[1]);
+          } else {
+            do_chunk(ra, ch, nullptr);
+            if (two) do_chunk(rb, ch + 4, nullptr);
+          }
         }
         if (p.S > 1) {
           __threadfence();
-          g2_bar_sync(1, EPI_THREADS);
+          g2_bar_sync(1, G2_EPI_THREADS);
           if (threadIdx.x == 64) st_release(p.flags + tile_flag, ks == p.S - 1 ? 0 : ks + 1);
         }
       } else {
@@ -339,8 +370,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // The up half hands its values over through shared memory (double-buffered, one named barrier per chunk).
         const int i = (m0 >> 1) + (lrow & 63);
         const bool i_ok = i < (p.F >> 1);
-        float* buf0 = gu_stage + hsel * (2 * 16 * 64);
-        for (int ch = hsel; ch < nchunks; ch += 2, ++it) {
+        float* buf0 = gu_stage + csel * (2 * 16 * 64);
+        for (int ch = csel; ch < nchunks; ch += 4, ++it) {
           if (n0 + ch * 16 >= p.T) break;
           uint32_t rr[16];
           tmem_ld16(taddr + ch * 16, rr);
@@ -350,7 +381,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 16; ++j) buf[j * 64 + (lrow - 64)] = __uint_as_float(rr[j]);
           }
-          g2_bar_sync(2 + hsel, 128);
+          g2_bar_sync(2 + csel, 128);
           if (q < 2 && i_ok) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -475,7 +506,7 @@ static Plan2 g2_plan(const myr_gemm_args* a) {
       for (int P = 1; P <= 4; P *= 2) {
         if (f_p > 0 ? P != f_p : P != 1) continue;  // multicast across pairs measured no gain on B200 (L2 already merges)
         for (int S = 1; S <= 4; ++S) {
-          if (f_s > 0 && S != f_s) continue;
+          if (f_s > 0 ? S != f_s : S != 1) continue;  // ordered split-K serialises the epilogues of a tile's splits: measured a loss
           if (S > 1 && (!split_ok || mode != 0 || (S - 1) * ceil_div(kb, S) >= kb || kb / S < 8)) continue;
           Plan2 pl;
           pl.row_mode = mode;
@@ -516,11 +547,18 @@ bool gemm2_eligible(const myr_gemm_args* a, int nbatch) {
   return true;
 }
 
-int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream) {
+int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled) {
   const Plan2 pl = g2_plan(a);
+  *handled = 1;
   if (pl.BN == 0) {
     set_error("gemm2: no plan for T=%d F=%d K=%d", a->T, a->F, a->K);
     return MYR_ERR_UNSUPPORTED;
+  }
+  // few output tiles (o_proj / down_proj / ViT proj / fc2 at batch 4: 36-48 tiles of 256 x 176 for 74 CTA pairs): the stream-K
+  // kernel of gemm.cu, which splits K over all 148 SMs, is faster there (profiles/r2_gemm2_sweep.md)
+  if (pl.n_units < env_int("MYR_G2_MIN_UNITS", 60) && env_int("MYR_G2_MODE", -1) < 0) {
+    *handled = 0;
+    return MYR_OK;
   }
   const void* pa = pl.row_mode ? a->x : a->w;
   const void* pb = pl.row_mode ? a->w : a->x;

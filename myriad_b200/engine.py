@@ -195,7 +195,7 @@ class MyriadEngine:
             pl = "llama_model.base_model.model.model.layers.%d.self_attn." % i
             if self.FUSED_LLAMA and self.d.lora_r > 0:
                 qkv_rows += [sd[pl + "q_proj.lora_A.default.weight"], sd[pl + "v_proj.lora_A.default.weight"]]
-            L.wqkv = _h(torch.cat(qkv_rows), dev)
+            L.wqkv = _h(torch.cat([t.to(dev) for t in qkv_rows]), dev)  # frozen rows may sit on the host, trainable LoRA rows on the device
             del qkv_rows
             L.wo = _h(sd[lp + "self_attn.o_proj.weight"], dev)
             g_, u_ = _h(sd[lp + "mlp.gate_proj.weight"], dev), _h(sd[lp + "mlp.up_proj.weight"], dev)
@@ -218,7 +218,7 @@ class MyriadEngine:
                     L.lora.bq = _h(sd[pl + "q_proj.lora_B.default.weight"], dev)
                     L.lora.bv = _h(sd[pl + "v_proj.lora_B.default.weight"], dev)
                 else:
-                    L.lora.a = _h(torch.cat([sd[pl + "q_proj.lora_A.default.weight"], sd[pl + "v_proj.lora_A.default.weight"]]), dev)
+                    L.lora.a = _h(torch.cat([sd[pl + "q_proj.lora_A.default.weight"].to(dev), sd[pl + "v_proj.lora_A.default.weight"].to(dev)]), dev)
                     L.lora.bq = _h(sd[pl + "q_proj.lora_B.default.weight"] * s, dev)
                     L.lora.bv = _h(sd[pl + "v_proj.lora_B.default.weight"] * s, dev)
             W.layers.append(L)

@@ -16,6 +16,7 @@ Gradient activations are fp16 GEMM operands, so the loss is scaled (GradScaler s
 weight-gradient epilogues / the optimizer unscale in fp32.
 """
 import math
+import os
 
 import torch
 
@@ -40,6 +41,9 @@ class MyriadTrainer(MyriadEngine):
         # path. 0.0 = off (parity runs against the oracle use a shared mask or no dropout). The mask stream is keyed by
         # (dropout_seed, forward count, layer, branch), see _lora_drop_offset.
         self.lora_dropout, self.dropout_seed, self.fwd_count = float(lora_dropout), int(dropout_seed), 0
+        self.overlap_allreduce = True
+        self._early = None
+        self.supervised_rows_only = True  # lm_head / clamp-CE only on the rows that carry a target (False: all positions, as the reference)
         self._sd_for_flat = sd
         super().__init__(sd, dims, device, max_batch, max_seq)
         self.loss_scale = float(loss_scale)
@@ -185,7 +189,21 @@ class MyriadTrainer(MyriadEngine):
         if self.d.lora_r:  # trainer keeps B unscaled (scale applied in the GEMM epilogue), refreshed from the flat buffer
             for L in self.llw.layers:
                 L.lora.scale = self.d.lora_alpha / self.d.lora_r
+        # The frozen projections are also kept TRANSPOSED ([K_in, F_out] -> rows = input features): the input-gradient GEMM
+        # dX = dY W then has both operands K-major and runs on the CTA-pair kernel (csrc/gemm2.cu) like the forward, instead of
+        # the MN-major operand path. Costs one more fp16 copy of the LLaMA linear weights (12.9 GB of the 180 GB).
+        self.dgrad_transposed = os.environ.get("MYR_DGRAD_T", "1") != "0"
+        if self.dgrad_transposed:
+            for L in self.llw.layers:
+                L.wqkv_t, L.wo_t = L.wqkv.t().contiguous(), L.wo.t().contiguous()
+                L.wgu_t, L.wd_t = L.wgu.t().contiguous(), L.wd.t().contiguous()
         self._refresh_late()
+
+    def _dgrad(self, dy, L, name, **kw):
+        """dX = dY W for one of the frozen LLaMA projections (name in wqkv / wo / wgu / wd)."""
+        if self.dgrad_transposed:
+            return K.gemm(dy, getattr(L, name + "_t"), **kw)
+        return K.gemm(dy, getattr(L, name), w_mn_major=True, **kw)
 
     def export_state_dict(self):
         out = {}
@@ -494,7 +512,8 @@ class MyriadTrainer(MyriadEngine):
         return dq32, d_ckv
 
     # ------------------------------------------------------------------------------ LLaMA with saved activations
-    def _llama_train_fwd(self, embeds32, kv_len, tp):
+    def _llama_train_fwd(self, embeds32, kv_len, tp, sup_idx=None):
+        """-> fp32 logits of the rows named by sup_idx (int32 [R], device) or of all T rows (sup_idx None)."""
         l, dev = self.d.llama, self.dev
         B, S, D = embeds32.shape
         H, dh, T = l.heads, l.head_dim, B * S
@@ -540,7 +559,14 @@ class MyriadTrainer(MyriadEngine):
         tp.h_final = h
         x16 = self._e(T, D)
         K.norm(h, self.llw.norm, None, l.eps, rms=True, out16=x16)
-        return K.gemm(x16, self.llw.lm_head, out_dtype=F32)  # [T, V] fp32 (modeling_llama.py:690)
+        tp.sup_idx = sup_idx
+        if sup_idx is not None:
+            # the reference runs lm_head on every position (modeling_llama.py:690) and the loss then ignores all but the
+            # supervised ones (labels -100): only those rows' logits exist here ([R, V] instead of [T, V], R ~ T / 10)
+            xs = self._e(sup_idx.numel(), D)
+            K.index_rows(x16, xs, sup_idx, D)
+            x16 = xs
+        return K.gemm(x16, self.llw.lm_head, out_dtype=F32)  # [R | T, V] fp32
 
     def _lora_drop_offset(self, layer, branch, n):
         """Start of the mask stream of (this forward, layer, branch q / v): streams never overlap within a run."""
@@ -554,24 +580,28 @@ class MyriadTrainer(MyriadEngine):
         T = B * S
         inv_scale = 1.0 / self.loss_scale
         d_x = K.gemm(dlogits16, self.llw.lm_head, w_mn_major=True, out_dtype=F32)
+        if tp.sup_idx is not None:  # rows without a target get no gradient from the loss
+            d_all = torch.zeros(T, D, device=self.dev, dtype=F32)
+            K.index_rows(d_x, d_all, tp.sup_idx, D, scatter=True)
+            d_x = d_all
         dh32, dh16 = self._norm_bwd(tp.h_final, d_x, self.llw.norm, l.eps, rms=True)
         att_scale = 1.0 / math.sqrt(dh)
         for li in range(l.layers - 1, -1, -1):
             L, Sv = self.llw.layers[li], tp.ll[li]
             kc, vc = self.kcache[li], self.vcache[li]
-            d_act = K.gemm(dh16, L.wd, w_mn_major=True)
+            d_act = self._dgrad(dh16, L, "wd")
             d_gu = self._e(T, 2 * l.inter)
             K.swiglu_bwd(Sv.gu, d_act, d_gu, T, l.inter)
-            d_x2 = K.gemm(d_gu, L.wgu, w_mn_major=True, out_dtype=F32)
+            d_x2 = self._dgrad(d_gu, L, "wgu", out_dtype=F32)
             dmid32, dmid16 = self._norm_bwd(Sv.h_mid, d_x2, L.n2, l.eps, rms=True, add=dh32)
-            d_ctx = K.gemm(dmid16, L.wo, w_mn_major=True)
+            d_ctx = self._dgrad(dmid16, L, "wo")
             dqkv = self._e(T, 3 * D)
             st = (3 * D, S * 3 * D)
             cst = (kc.stride(1), kc.stride(0))
             self._attn_bwd((Sv.qkv, *st), (kc, *cst), (vc, *cst), d_ctx, (dqkv, *st), (dqkv[:, D:], *st), (dqkv[:, 2 * D:], *st),
                            B, H, S, S, dh, att_scale, True, tp.kv_len)
             K.rope_bwd(dqkv, T, H, dh, tp.pos, self.llw.cos, self.llw.sin)
-            d_x1 = K.gemm(dqkv, L.wqkv, w_mn_major=True, out_dtype=F32)
+            d_x1 = self._dgrad(dqkv, L, "wqkv", out_dtype=F32)
             if L.lora is not None:
                 r = self.d.lora_r
                 p = "llama_model.base_model.model.model.layers.%d.self_attn." % li
@@ -622,14 +652,23 @@ class MyriadTrainer(MyriadEngine):
         kv_len = (Lw + text_mask.sum(-1)).to(torch.int32).to(dev)
         # targets myriad.py:406-416, shifted by one for next-token prediction (modeling_llama.py:697-703)
         targets = torch.cat([torch.full((B, Lw), -100, dtype=torch.long), text_ids.masked_fill(text_ids == l.eos, -100)], 1)
-        shifted = torch.cat([targets[:, 1:], torch.full((B, 1), -100, dtype=torch.long)], 1).reshape(-1).to(dev)
-        logits = self._llama_train_fwd(emb, kv_len, tp)
-        T = B * Ltot
+        shifted = torch.cat([targets[:, 1:], torch.full((B, 1), -100, dtype=torch.long)], 1).reshape(-1)
+        sup = torch.nonzero(shifted != -100).reshape(-1)
+        if self.supervised_rows_only and 0 < sup.numel():
+            sup_idx = sup.to(torch.int32).to(dev)
+            shifted = shifted[sup]
+        else:
+            sup_idx = None
+        shifted = shifted.to(dev)
+        logits = self._llama_train_fwd(emb, kv_len, tp, sup_idx)
+        T = logits.shape[0]
         row_loss, stats, loss_out = self._e(T, dtype=F32), self._e(T, 2, dtype=F32), self._e(2, dtype=F32)
         K.clamp_ce_fwd(logits, shifted, row_loss, stats, loss_out)
         dlogits = self._e(T, l.vocab)
         K.clamp_ce_bwd(logits, shifted, stats, loss_out, self.loss_scale, dlogits)
         d_emb = self._llama_train_bwd(dlogits, tp, B)  # fp32 [T, D]
+        if stage == 2:
+            self._early_allreduce()  # no VETokenizer in this stage: its (zero) gradients and the LoRA ones are already final
         # ---- inputs_embeds -> image-token groups (myriad.py:249-266 concatenation order: Q-Former tokens, then VETokenizer)
         n_before = 1 + ids_before.shape[-1]
         flat = d_emb.reshape(-1)
@@ -641,6 +680,7 @@ class MyriadTrainer(MyriadEngine):
             K.colsum(flat[off:], D, Ltot * D, B, 1, 9 * D, self.grad("VETokenizer.base_prompts").reshape(-1), scale=inv_scale)
             d_tok16 = self._cast16(flat[off + 9 * D:], 9, D, src_ld=D, src_gs=Ltot * D, groups=B)
             self._ve_head_bwd(self.tokw, tp.tok, d_tok16, B)
+            self._early_allreduce()
         d_h = K.gemm(d_proj16, self.qfw.proj_w, w_mn_major=True, out_dtype=F32)  # llama_proj is frozen: dX only
         dq32, d_ckv = self._qformer_bwd(d_h, tp)
         if stage in (1, 2):
@@ -656,11 +696,34 @@ class MyriadTrainer(MyriadEngine):
                       self.grad("expert_adaptor.conv2.weight"), rows, Dv, rk, inv_scale)
         return loss_out[0]
 
+    def _early_allreduce(self):
+        """Data parallel: the flat gradient buffer is laid out [adaptor | VEInstructor | VETokenizer | LoRA]; from the VETokenizer
+        segment on (97 % of the bytes: the 5x5 head's 420 MB) every gradient is final once the tokenizer head's backward has
+        run, while the Q-Former / VEInstructor / adaptor backward is still ahead. That tail is all-reduced NOW, asynchronously
+        on NCCL's stream, and overlaps the rest of the backward; optimizer_step reduces the small head of the buffer."""
+        import torch.distributed as dist
+        self._early = None
+        if not (self.overlap_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        key = "VETokenizer.meta_net.0.weight"
+        if key not in self.segments:
+            return
+        split = self.segments[key][0]
+        work = dist.all_reduce(self.flat_grads[split:], op=dist.ReduceOp.SUM, async_op=True)
+        self._early = (split, work)
+
     def optimizer_step(self, lr=None):
-        """DDP gradient averaging (runner_base.py:96-98: one all-reduce of the flat buffer over NCCL/NVLink) + fused AdamW
-        (runner_base.py:105-139) + refresh of the fp16 operand copies."""
+        """DDP gradient averaging (runner_base.py:96-98: all-reduce of the flat buffer over NCCL/NVLink, the bulk of it
+        overlapped with the backward, see _early_allreduce) + fused AdamW (runner_base.py:105-139) + refresh of the fp16
+        operand copies."""
         from .dp import allreduce_flat_grads
-        mean_scale = allreduce_flat_grads(self.flat_grads)  # sum over ranks; 1 / world folded into the optimizer's unscale
+        early, self._early = getattr(self, "_early", None), None
+        if early is not None:
+            split, work = early
+            mean_scale = allreduce_flat_grads(self.flat_grads[:split])
+            work.wait()
+        else:
+            mean_scale = allreduce_flat_grads(self.flat_grads)  # sum over ranks; 1 / world folded into the optimizer's unscale
         self._poll_overflow_flags(block=len(self._flag_pending) >= len(self._flag_ring))
         self.opt_step += 1
         hp = self.hp

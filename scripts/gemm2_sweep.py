@@ -41,6 +41,7 @@ GROUPS = {
             for st, nw in ((6, 8), (4, 8), (3, 8), (2, 8), (6, 1))] +
            [("ll_gu", 0, bn, 1, 1, {"NW": "2"}) for bn in (96, 128, 176, 256)] + [("big_gu", 0, bn, 1, 1, {"NW": "2"}) for bn in (128, 192, 256)],
     "abl": [("ll_gu", 0, bn, 1, 1, {"NW": "2", "MYR_G2_DBG": str(d)}) for bn in (176,) for d in (0, 1, 2, 4, 6, 8, 3, 5)],
+    "tl": [("ll_gu", 0, 176, 1, 1, {"NW": "2", "MYR_G2_DBG": str(d)}) for d in (16, 17, 21)],
     "m1": [("vit_fc1", 1, 256, 1, 1), ("ll_gu", 1, 256, 1, 1), ("big_gu", 1, 256, 1, 1), ("big_down", 1, 256, 1, 1)],
 }
 
@@ -117,6 +118,13 @@ def run_group(name):
         K.gemm(x, ws[0], bias=bias, act=act, res=res, out=out)
         K.lib().myr_gemm_set_trace(ctypes.c_void_p(0))
         torch.cuda.synchronize()
+        if int(os.environ.get("MYR_G2_DBG", "0")) & 16:
+            x = tr[888:888 + 192].cpu()
+            t00 = int(x[0])
+            fmt = lambda v: " ".join("%.2f" % ((int(a) - t00) / 1e3) for a in v[:40])
+            print("TL leader issue  us:", fmt(x[0:64]))
+            print("TL leader mmardy us:", fmt(x[64:128]))
+            print("TL peer   issue  us:", fmt(x[128:192]), flush=True)
         t = tr[:148 * 6].reshape(148, 6).cpu()
         live = t[:, 0] > 0
         tl = ""

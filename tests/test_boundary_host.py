@@ -240,3 +240,32 @@ def test_eval_postprocessing_records():
     assert recs[0]["anomaly_score"] == str(round(int(0.8 * 255) / 255.0, 4))
     assert summarize(recs) == {"n": 2, "errors": 1, "accuracy": 0.5}
     assert yes_no_error("No defects", False) == "0" and STOP_WORD_IDS == ((835,), (2277, 29937))
+
+
+def test_reference_checkpoint_loader_reads_the_reference_file_layout(tmp_path, monkeypatch):
+    """minigpt4/models/checkpoints.py against files laid out like the reference's (eva_vit.py:429-436, blip2.py:91-110,
+    myriad.py:193-217): keys come back under the reference state_dict names; a missing file is a clear error."""
+    from minigpt4.models.checkpoints import load_reference_checkpoints
+    from myriad_b200 import synthetic as syn
+    d = syn.tiny_dims()
+    sd = syn.make_state_dict(d, 0)
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("pretrained_models")
+    torch.save({k[len("visual_encoder."):]: v for k, v in sd.items() if k.startswith("visual_encoder.")}, "pretrained_models/eva_vit_g.pth")
+    torch.save({"model": {k: v for k, v in sd.items() if k.startswith(("Qformer.", "ln_vision.")) or k == "query_tokens"}}, "blip2.pth")
+    torch.save({"model": {"llama_proj.weight": sd["llama_proj.weight"], "llama_proj.bias": sd["llama_proj.bias"]}},
+               "pretrained_models/pretrained_minigpt4_7b.pth")
+    os.makedirs("vicuna")
+    ll = {k[len("llama_model."):]: v for k, v in sd.items() if k.startswith("llama_model.")}
+    keys = sorted(ll)
+    torch.save({k: ll[k] for k in keys[:len(keys) // 2]}, "vicuna/pytorch_model-00001-of-00002.bin")
+    torch.save({k: ll[k] for k in keys[len(keys) // 2:]}, "vicuna/pytorch_model-00002-of-00002.bin")
+    got = load_reference_checkpoints(d, "vicuna", "blip2.pth")
+    frozen = [k for k in sd if not k.startswith(("expert_adaptor.", "VEInstructor.", "VETokenizer.")) and ".lora_" not in k]
+    assert sorted(got) == sorted(frozen)
+    assert all(torch.equal(got[k], sd[k]) for k in frozen)
+    with pytest.raises(FileNotFoundError):
+        load_reference_checkpoints(d, "vicuna", "missing.pth")
+    from minigpt4.models.tokenizer import load_llama_tokenizer
+    with pytest.raises(FileNotFoundError):
+        load_llama_tokenizer("vicuna", 32000)  # a real weights directory without tokenizer files must not fall back silently

@@ -190,6 +190,7 @@ def test_train_py_sequence_runs_two_iterations(tmp_path, monkeypatch):
     path.write_text(yaml.safe_dump(cfg))
     import minigpt4.tasks as tasks
     from minigpt4.common.config import Config
+    from minigpt4.common.optims import LinearWarmupCosineLRScheduler, LinearWarmupStepLRScheduler  # noqa: F401  (train.py:22-25)
     from minigpt4.common.registry import registry
     from minigpt4.common.utils import now
     import minigpt4.datasets.builders  # noqa: F401  (train.py:28-32 star-imports these five packages for their registrations)
