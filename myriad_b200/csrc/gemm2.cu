@@ -502,7 +502,7 @@ static Plan2 g2_plan(const myr_gemm_args* a) {
     const int gran = (mode && swiglu) ? 128 : 16;
     for (int bn = gran; bn <= 256; bn += gran) {
       if (f_bn > 0 && bn != f_bn) continue;
-      if (bn < 64 && bn != f_bn) continue;
+      if (bn < 128 && bn != f_bn) continue;  // narrower tiles move more operand bytes per flop than an SM can take in
       for (int P = 1; P <= 4; P *= 2) {
         if (f_p > 0 ? P != f_p : P != 1) continue;  // multicast across pairs measured no gain on B200 (L2 already merges)
         for (int S = 1; S <= 4; ++S) {
@@ -556,7 +556,10 @@ int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled) {
   }
   // few output tiles (o_proj / down_proj / ViT proj / fc2 at batch 4: 36-48 tiles of 256 x 176 for 74 CTA pairs): the stream-K
   // kernel of gemm.cu, which splits K over all 148 SMs, is faster there (profiles/r2_gemm2_sweep.md)
-  if (pl.n_units < env_int("MYR_G2_MIN_UNITS", 60) && env_int("MYR_G2_MODE", -1) < 0) {
+  // ... and so is a launch whose last wave of tiles would leave most CTA pairs idle (ViT qkv at batch 4: 102 tiles = 1.38 waves)
+  const int waves = ceil_div(pl.n_units, pl.n_clusters);
+  const double wave_eff = (double)pl.n_units / ((double)waves * pl.n_clusters);
+  if ((pl.n_units < env_int("MYR_G2_MIN_UNITS", 60) || wave_eff < 0.8) && env_int("MYR_G2_MODE", -1) < 0) {
     *handled = 0;
     return MYR_OK;
   }

@@ -44,9 +44,15 @@ b2 = torch.zeros(1408, device=dev).half()
 xr = torch.zeros(T, 1408, device=dev)
 m = K.gemm(h, w1, bias=b1, act=K.ACT_GELU)
 K.gemm(m, w2, bias=b2, res=xr, out=xr)
-# LLaMA prefill GEMM (T = 524): gate/up + SwiGLU
+# LLaMA prefill GEMMs (T = 524): gate/up + SwiGLU and qkv on the CTA-pair kernel (gemm2.cu), o_proj + residual (few tiles: gemm.cu)
 hp = torch.randn(524, 4096, device=dev).half()
 K.gemm(hp, wgu, act=K.ACT_SWIGLU)
+K.gemm(hp, wq)
+rp = torch.zeros(524, 4096, device=dev)
+K.gemm(hp, wo, res=rp, out=rp)
+# Q-Former cross-attention K/V projection of all six cross layers (T = 1028, F = 9216)
+wkv = (torch.randn(9216, 1408, device=dev) * 0.02).half()
+K.gemm(h, wkv, bias=torch.zeros(9216, device=dev).half())
 # ViT attention (dh = 88, N = 257), LLaMA prefill attention (dh = 128, S = 131, causal)
 D = 1408
 qkv = torch.randn(T, 3 * D, device=dev).half()
@@ -59,6 +65,13 @@ ql = torch.randn(B * S, 3 * Dl, device=dev).half()
 ol = torch.empty(B * S, Dl, device=dev, dtype=torch.float16)
 sl = (3 * Dl, S * 3 * Dl, 128)
 K.attention(ql, ql[:, Dl:], ql[:, 2 * Dl:], ol, B, 32, S, S, 128, 1 / math.sqrt(128), sl, sl, sl, (Dl, S * Dl, 128), causal=True)
+# long-sequence prefill attention of the sweep (BASELINE configs[4]): S = 2048, causal and full
+S2 = 2048
+q2 = torch.randn(B * S2, 3 * Dl, device=dev).half()
+o2 = torch.empty(B * S2, Dl, device=dev, dtype=torch.float16)
+s2 = (3 * Dl, S2 * 3 * Dl, 128)
+for causal in (True, False):
+    K.attention(q2, q2[:, Dl:], q2[:, 2 * Dl:], o2, B, 32, S2, S2, 128, 1 / math.sqrt(128), s2, s2, s2, (Dl, S2 * Dl, 128), causal=causal)
 # decode attention (one launch per layer and step): 4 sequences, 32 heads, 160 cached tokens
 kc = torch.randn(B, 256, Dl, device=dev).half()
 vc = torch.randn(B, 256, Dl, device=dev).half()
