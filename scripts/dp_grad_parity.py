@@ -64,19 +64,16 @@ def main():
               "%.2e (%s)" % (world, e, worst[0], worst[1]), flush=True)
     ok &= worst[0] < 5e-2  # fp16 operands: the two batches split the token dimension of the wgrad GEMMs differently
     # (b) a different stage on every rank vs the mean of the separately computed per-rank gradients
-    tr.overlap_allreduce = True
     stages = [(1, 2, 0)[r % 3] for r in range(world)]
-    tr.forward_backward(image_all[sl].to(dev), maps_all[sl].to(dev), stages[rank], ids_b, ids_a, text_all[sl], tmask_all[sl])
-    mine = tr.flat_grads.clone()
-    got = reduced_grads(tr, world)
     tr.overlap_allreduce = False
     want = torch.zeros_like(got)
     for r in range(world):
         s2 = slice(r * Bp, (r + 1) * Bp)
         tr.forward_backward(image_all[s2].to(dev), maps_all[s2].to(dev), stages[r], ids_b, ids_a, text_all[s2], tmask_all[s2])
         want += tr.flat_grads / world
-        if r == rank:
-            assert torch.equal(tr.flat_grads, mine), "forward_backward is deterministic"
+    tr.overlap_allreduce = True  # the tail of the buffer is reduced asynchronously while the backward continues
+    tr.forward_backward(image_all[sl].to(dev), maps_all[sl].to(dev), stages[rank], ids_b, ids_a, text_all[sl], tmask_all[sl])
+    got = reduced_grads(tr, world)
     e = rel(got, want)
     o, shape, _ = tr.segments["VETokenizer.meta_net.15.weight"]
     n = int(torch.tensor(shape).prod())
