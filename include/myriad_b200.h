@@ -194,6 +194,12 @@ typedef struct {
                                             kernel prefetches the next layer's slice into L2 */
   int32_t kv_cap;                        /* 0, or an upper bound (<= 256, <= cache_len) on kv_len for this launch (and every replay
                                             of a graph holding it): K / V then arrive by TMA in 512 * kv_cap bytes of shared memory */
+  void* split_ws; size_t split_ws_bytes; /* optional workspace for LONG caches (cache_len > 256, kv_cap == 0): the cache is then cut
+                                            into 128-key chunks, one CTA each (K / V by TMA), whose partial (max, sum, P.V) results
+                                            meet here and are combined in chunk order by the last CTA of a (head, row) to arrive -
+                                            deterministic. Needs 16 + B * H * (4 + ceil(cache_len / 128) * 520) bytes, 16-byte
+                                            aligned, ZEROED once; the kernel leaves its counters at zero. NULL: one CTA walks the
+                                            whole cache. */
 } myr_decode_attn_args;
 int myr_decode_attention(const myr_decode_attn_args* args, void* stream);
 

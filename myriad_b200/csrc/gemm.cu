@@ -610,7 +610,8 @@ extern "C" size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K) {
   return COUNTER_BYTES + tiles * 4 * 256 * BM * sizeof(float);
 }
 
-int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter);  // gemv.cu
+int myr_gemv_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter);     // gemv.cu
+int myr_gemv_mt_dispatch(const myr_gemm_args* a, cudaStream_t stream, int* counter);  // gemv_mt.cu
 namespace myr {
 bool gemm2_eligible(const myr_gemm_args* a, int nbatch);  // gemm2.cu: CTA-pair kernel for the tensor-bound shapes
 int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled);
@@ -634,6 +635,18 @@ static bool gemv_eligible(const myr_gemm_args* a, int nbatch) {
   return a->T <= 4 && !a->x_mn_major && !a->w_mn_major && nbatch == 1 && a->scale_cols == 0 && !a->round_acc && !a->alpha_set &&
          a->out_group_rows == 0 && (a->act == MYR_ACT_NONE || a->act == MYR_ACT_SWIGLU) && a->K % 128 == 0 && a->K <= 32768 && a->bn_hint == 0 &&
          a->ksplit_hint == 0;
+}
+
+// 5 <= T <= 32 (decode steps of the throughput sweep's batches): weights AND tokens streamed through one ring (gemv_mt.cu)
+static bool gemv_mt_eligible(const myr_gemm_args* a, int nbatch) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MYR_GEMV_MT");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on && a->T >= 5 && a->T <= 32 && !a->x_mn_major && !a->w_mn_major && nbatch == 1 && a->scale_cols == 0 && !a->round_acc &&
+         !a->alpha_set && a->out_group_rows == 0 && (a->act == MYR_ACT_NONE || a->act == MYR_ACT_SWIGLU) && a->K % 128 == 0 &&
+         a->bn_hint == 0 && a->ksplit_hint == 0 && a->norm_ss == nullptr && a->post_out16 == nullptr && a->F >= 1024;
 }
 
 extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
@@ -664,6 +677,13 @@ extern "C" int myr_gemm_f16(const myr_gemm_args* a, void* stream_) {
     if (a->workspace != nullptr && a->workspace_bytes >= COUNTER_BYTES && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0)
       ctr = reinterpret_cast<int*>(a->workspace) + (MAX_COUNTERS - 1);
     return myr_gemv_dispatch(a, stream, ctr);
+  }
+  if (gemv_enabled() && gemv_mt_eligible(a, nbatch)) {
+    MYR_CHECK_ARG((a->res == nullptr || (a->ldr > 0)) && a->ldo > 0, "gemm: bad leading dimensions");
+    int* ctr = nullptr;
+    if (a->workspace != nullptr && a->workspace_bytes >= COUNTER_BYTES && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0)
+      ctr = reinterpret_cast<int*>(a->workspace) + (MAX_COUNTERS - 1);
+    return myr_gemv_mt_dispatch(a, stream, ctr);
   }
   if (a->norm_ss != nullptr || a->post_out16 != nullptr) {
     set_error("gemm: the RMSNorm hand-over exists on the small-batch path only (T <= 4, plain K-major operands, no hints)");

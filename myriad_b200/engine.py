@@ -376,7 +376,7 @@ class MyriadEngine:
             self._decode_graphs = {}
 
     def _llama_layer(self, L, li, h32, bufs, B, S, pos, kv_len, cache_off, cache_off_dev, Skv, causal, hand=None, next_gamma=None,
-                     kv_cap=0):
+                     kv_cap=0, split_ws=None):
         """LlamaDecoderLayer.forward modeling_llama.py:247-299 as 8 launches: RMSNorm -> qkv (+ LoRA A rows) GEMM -> RoPE +
         LoRA B + KV-cache append -> flash attention -> o_proj GEMM (+ residual) -> RMSNorm -> gate/up GEMM with fused
         SwiGLU -> down GEMM (+ residual). Weights are static, so each GEMM may prefetch them under the previous kernel."""
@@ -401,7 +401,8 @@ class MyriadEngine:
             # decode: rotary + LoRA-B + cache append + attention over the cache in one CUDA-core launch
             nxt = self.kcache.stride(0) if li + 1 < l.layers else 0
             K.decode_attention(qkv, B, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, kv_len, ctx, 1.0 / math.sqrt(dh),
-                               cache_off=cache_off, cache_off_dev=cache_off_dev, lora=lora, next_layer_stride=nxt, kv_cap=kv_cap)
+                               cache_off=cache_off, cache_off_dev=cache_off_dev, lora=lora, next_layer_stride=nxt, kv_cap=kv_cap,
+                               split_ws=split_ws)
         else:
             K.rope_cache(qkv, B, S, H, dh, pos, self.llw.cos, self.llw.sin, kc, vc, cache_off=cache_off,
                          cache_off_dev=cache_off_dev, lora=lora)
@@ -457,7 +458,7 @@ class MyriadEngine:
         for li, L in enumerate(self.llw.layers):
             nxt = self.llw.layers[li + 1].n1 if li + 1 < l.layers else self.llw.norm
             self._llama_layer(L, li, st.h32, st.bufs, B, 1, st.pos, st.kv_len, 0, st.cache_off, st.Skv, False, hand=hand, next_gamma=nxt,
-                              kv_cap=st.kv_cap if hand is not None else 0)
+                              kv_cap=st.kv_cap if hand is not None else 0, split_ws=st.attn_ws)
         if hand is not None:
             K.gemm(hand.yb, self.llw.lm_head, out=st.logits, w_static=True, norm_ss=(hand.ssb, l.eps))
         else:
@@ -522,6 +523,11 @@ class MyriadEngine:
         st.hand = _Obj()  # RMSNorm hand-over buffers of the small-batch path (o_proj -> gate/up, down_proj -> next qkv / lm_head)
         st.hand.ya, st.hand.yb = (torch.zeros(B, l.hidden, device=dev, dtype=F16) for _ in range(2))
         st.hand.ssa, st.hand.ssb = (torch.zeros(K.NORM_SS_FLOATS, device=dev, dtype=F32) for _ in range(2))
+        # long caches: decode attention runs one CTA per 128-key chunk and combines the partials here (zeroed once; the kernel
+        # leaves its arrival counters at zero)
+        st.attn_ws = None
+        if Skv > 256 and os.environ.get("MYR_ATTN_SPLIT", "1") != "0":
+            st.attn_ws = torch.zeros(K.decode_attn_split_bytes(B, l.heads, Skv), device=dev, dtype=torch.uint8)
         st.graph = None
         st.mega = self._mega_plan(st) if self._mega_ok(B, Skv) else None
         return st

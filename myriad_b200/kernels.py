@@ -245,11 +245,17 @@ class DecodeAttnArgs(ctypes.Structure):
         ("out", ctypes.c_void_p), ("ldo", ctypes.c_int64),
         ("next_layer_stride", ctypes.c_int64),
         ("kv_cap", ctypes.c_int32),
+        ("split_ws", ctypes.c_void_p), ("split_ws_bytes", ctypes.c_size_t),
     ]
 
 
+def decode_attn_split_bytes(B, H, cache_len):
+    """Workspace (zero-initialised by the caller, once) of the long-cache decode attention: counters + per-chunk partials."""
+    return B * H * (4 + ((cache_len + 127) // 128) * 520) + 64
+
+
 def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, scale, cache_off=0, cache_off_dev=None, lora=None,
-                     next_layer_stride=0, kv_cap=0):
+                     next_layer_stride=0, kv_cap=0, split_ws=None):
     """One new token per sequence: LoRA-B + RoPE + KV-cache append + attention over the cache in one launch."""
     a = DecodeAttnArgs()
     a.qkv, a.ldq = qkv.data_ptr(), qkv.stride(0)
@@ -268,6 +274,8 @@ def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, 
     a.out, a.ldo = out.data_ptr(), out.stride(0)
     a.next_layer_stride = next_layer_stride
     a.kv_cap = kv_cap
+    if split_ws is not None:
+        a.split_ws, a.split_ws_bytes = split_ws.data_ptr(), split_ws.numel() * split_ws.element_size()
     check(lib().myr_decode_attention(ctypes.byref(a), _stream()), "myr_decode_attention")
     return out
 

@@ -184,3 +184,103 @@ def test_gemv_rmsnorm_hand_over(K, O):
     K.norm(h, gamma, None, 1e-6, rms=True, out16=x16)
     y2 = K.gemm(x16, w, out_dtype=torch.float32, w_static=True)
     close(y, y2, 5e-4, "hand-over vs norm kernel + projection")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 5 <= T <= 32: weights and tokens streamed through one ring (csrc/gemv_mt.cu)
+MT_SHAPES = [(16, 4096, 4096), (32, 12304, 4096), (5, 4096, 11008), (9, 32000, 4096), (24, 4096, 4096), (17, 1024, 128),
+             (32, 4096, 11008), (8, 1100, 640), (31, 12304, 4096)]
+
+
+@pytest.mark.parametrize("T,F,Kd", MT_SHAPES)
+def test_gemv_mt_vs_fp32_and_tensor_core_path(K, T, F, Kd):
+    x, w = rnd(T, Kd, seed=1).half().to(dev()), (rnd(F, Kd, seed=2) / Kd ** 0.5).half().to(dev())
+    b = rnd(F, seed=3).half().to(dev())
+    r32 = rnd(T, F, seed=4).to(dev())
+    ref = x.float() @ w.float().t() + b.float() + r32
+    n0 = K.launch_count()
+    y1 = K.gemm(x, w, bias=b, res=r32, out_dtype=torch.float32, w_static=True)
+    assert K.launch_count() - n0 == 1, "one launch: no split-tile reduce, no workspace pass"
+    y2 = K.gemm(x, w, bias=b, res=r32, out_dtype=torch.float32, w_static=True)
+    close(y1, ref, 1e-3, "gemv_mt")
+    assert torch.equal(y1, y2), "fixed-order reduction must be reproducible"
+    old = K.set_gemv(False)
+    try:
+        y3 = K.gemm(x, w, bias=b, res=r32, out_dtype=torch.float32)
+    finally:
+        K.set_gemv(old)
+    close(y1, y3, 1e-3, "gemv_mt vs tcgen05")
+    # fp16 output, no residual / bias, padded row strides on both operands, in-place fp32 residual
+    xp = torch.zeros(T, Kd + 64, device=dev(), dtype=torch.float16)
+    xp[:, :Kd] = x
+    wp = torch.zeros(F, Kd + 8, device=dev(), dtype=torch.float16)
+    wp[:, :Kd] = w
+    y4 = K.gemm(xp[:, :Kd], wp[:, :Kd], K=Kd)
+    close(y4, x.float() @ w.float().t(), 2e-3, "gemv_mt fp16 out, strided operands")
+    acc = r32.clone()
+    K.gemm(x, w, res=acc, out=acc, w_static=True)
+    close(acc, x.float() @ w.float().t() + r32, 1e-3, "gemv_mt in-place residual")
+
+
+@pytest.mark.parametrize("T,I,Kd", [(16, 11008, 4096), (32, 11008, 4096), (5, 1024, 640), (20, 1088, 4096), (12, 1032 * 8 // 8 // 64 * 64, 256)])
+def test_gemv_mt_swiglu(K, T, I, Kd):
+    x = rnd(T, Kd, seed=1).half().to(dev())
+    g, u = (rnd(I, Kd, seed=2) / Kd ** 0.5).half(), (rnd(I, Kd, seed=3) / Kd ** 0.5).half()
+    n0 = K.launch_count()
+    y = K.gemm(x, _interleave64(g, u).to(dev()), act=K.ACT_SWIGLU, w_static=True)
+    assert K.launch_count() - n0 == 1
+    assert y.shape == (T, I) and y.dtype == torch.float16
+    gf, uf = x.float().cpu() @ g.float().t(), x.float().cpu() @ u.float().t()
+    close(y, torch.nn.functional.silu(gf.half().float()) * uf.half().float(), 3e-3, "gemv_mt swiglu")
+    old = K.set_gemv(False)
+    try:
+        y_tc = K.gemm(x, _interleave64(g, u).to(dev()), act=K.ACT_SWIGLU)
+    finally:
+        K.set_gemv(old)
+    close(y, y_tc, 2e-3, "gemv_mt swiglu vs tcgen05")
+    assert (y != y_tc).float().mean().item() < 0.05
+
+
+def test_gemv_mt_dependent_chain_in_cuda_graph(K):
+    """o_proj -> gate/up -> down of one decode step at batch 16 as dependent launches (programmatic dependent launch: weights
+    are requested before the predecessor finishes, tokens after): eager == CUDA-graph replay, bit for bit, over 3 replays."""
+    T, D, I = 16, 4096, 11008
+    ctx = rnd(T, D, seed=1).half().to(dev())
+    wo = (rnd(D, D, seed=2) / D ** 0.5).half().to(dev())
+    g, u = (rnd(I, D, seed=3) / D ** 0.5).half(), (rnd(I, D, seed=4) / D ** 0.5).half()
+    wgu = _interleave64(g, u).to(dev())
+    wd = (rnd(D, I, seed=5) / I ** 0.5).half().to(dev())
+    h0 = rnd(T, D, seed=6).to(dev())
+    x16 = torch.empty(T, D, device=dev(), dtype=torch.float16)
+    act = torch.empty(T, I, device=dev(), dtype=torch.float16)
+    gamma = torch.ones(D, device=dev())
+
+    def chain(h):
+        K.gemm(ctx, wo, res=h, out=h, w_static=True)
+        K.norm(h, gamma, None, 1e-6, rms=True, out16=x16)
+        K.gemm(x16, wgu, act=K.ACT_SWIGLU, out=act, w_static=True)
+        K.gemm(act, wd, res=h, out=h, w_static=True)
+
+    h_e = h0.clone()
+    chain(h_e)
+    torch.cuda.synchronize()
+    hf = h0.float().cpu() + ctx.float().cpu() @ wo.float().cpu().t()
+    xn = (hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-6)).half().float()
+    a = torch.nn.functional.silu((xn @ g.float().t()).half().float()) * (xn @ u.float().t()).half().float()
+    ref = hf + a.half().float() @ wd.float().cpu().t()
+    close(h_e, ref, 2e-3, "decode-step chain at batch 16")
+    h_g = h0.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        chain(h_g)  # warm-up on the side stream
+        h_g.copy_(h0)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            chain(h_g)
+    torch.cuda.current_stream().wait_stream(s)
+    for _ in range(3):
+        h_g.copy_(h0)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(h_g, h_e), "CUDA-graph replay must equal eager launches"

@@ -373,7 +373,14 @@ def test_decode_attention_bench_shape(K, O, kv_cap, off):
     _decode_attention_case(K, O, True, kv_cap, B=4, H=32, Smax=163, past=[off, off, off - 7, 3], off=off)
 
 
-def _decode_attention_case(K, O, lora, kv_cap, B, H, Smax, past, off):
+@pytest.mark.parametrize("off", [280, 600, 1023, 1024, 2070])
+def test_decode_attention_long_cache_split(K, O, off):
+    """Caches beyond 256 tokens (the sweep's S = 256 / 1024 / 2048): one CTA per 128-key chunk + ordered combine, against the same
+    references; `off` puts the new token's slot inside a chunk, at a chunk's last key, at a chunk's first key, near the end."""
+    _decode_attention_case(K, O, True, 0, B=2, H=4, Smax=2080, past=[off, off - 5], off=off, split=True)
+
+
+def _decode_attention_case(K, O, lora, kv_cap, B, H, Smax, past, off, split=False):
     """myr_decode_attention (one launch per decode step and layer) against the prefill pair myr_rope_cache + myr_attention_fwd
     on the same cache, and against the oracle's rotary / attention arithmetic."""
     torch.manual_seed(4)
@@ -388,7 +395,7 @@ def _decode_attention_case(K, O, lora, kv_cap, B, H, Smax, past, off):
     # make "past" keys of each row live in slots [off - past, off)
     pos = torch.tensor([p for p in past], dtype=torch.int32)
     kv_len = torch.tensor([off + 1] * B, dtype=torch.int32)
-    cos, sin = O.rope_tables(dh, 256)
+    cos, sin = O.rope_tables(dh, max(256, Smax + 8))
     half = dh // 2
     cosd, sind = cos[:, :half].contiguous().to(dev()), sin[:, :half].contiguous().to(dev())
     lo = (bq.to(dev()), bv.to(dev()), r, 2.0) if lora else None
@@ -401,8 +408,12 @@ def _decode_attention_case(K, O, lora, kv_cap, B, H, Smax, past, off):
                 kv_len=kv_len.to(dev()))
     kc2, vc2 = kc.to(dev()).clone(), vc.to(dev()).clone()
     out = torch.empty(B, D, device=dev(), dtype=torch.float16)
-    K.decode_attention(qkv.to(dev()), B, H, dh, pos.to(dev()), cosd, sind, kc2, vc2, kv_len.to(dev()), out, 1.0 / math.sqrt(dh),
-                       cache_off=off, lora=lo, kv_cap=kv_cap)
+    ws = torch.zeros(K.decode_attn_split_bytes(B, H, Smax), device=dev(), dtype=torch.uint8) if split else None
+    for rep in range(2 if split else 1):  # second launch: the arrival counters must have been left at zero
+        K.decode_attention(qkv.to(dev()), B, H, dh, pos.to(dev()), cosd, sind, kc2, vc2, kv_len.to(dev()), out, 1.0 / math.sqrt(dh),
+                           cache_off=off, lora=lo, kv_cap=kv_cap, split_ws=ws)
+    if split:
+        assert int(ws[:B * H * 4].view(torch.int32).abs().sum()) == 0
     close(kc2, kc1, 1e-3, "appended k")
     close(vc2, vc1, 1e-3, "appended v")
     print("cache append: %d k / %d v values differ in the last bit from myr_rope_cache" % (
