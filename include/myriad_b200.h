@@ -194,14 +194,15 @@ typedef struct {
                                             kernel prefetches the next layer's slice into L2 */
   int32_t kv_cap;                        /* 0, or an upper bound (<= 256, <= cache_len) on kv_len for this launch (and every replay
                                             of a graph holding it): K / V then arrive by TMA in 512 * kv_cap bytes of shared memory */
-  void* split_ws; size_t split_ws_bytes; /* optional workspace for LONG caches (cache_len > 256, kv_cap == 0): the cache is then cut
-                                            into 128-key chunks, one CTA each (K / V by TMA), whose partial (max, sum, P.V) results
-                                            meet here and are combined in chunk order by the last CTA of a (head, row) to arrive -
-                                            deterministic. Needs 16 + B * H * (4 + ceil(cache_len / 128) * 520) bytes, 16-byte
-                                            aligned, ZEROED once; the kernel leaves its counters at zero. NULL: one CTA walks the
-                                            whole cache. */
+  void* split_ws; size_t split_ws_bytes; /* optional workspace for LONG caches (cache_len > 256, kv_cap == 0, B <= 128): persistent CTAs
+                                            then stream the flat list of 128-key chunks of all (row, head) pairs (K / V by TMA, online
+                                            softmax); (row, head)s cut between CTAs leave partial (max, sum, P.V) results here, combined
+                                            in order by the last one to arrive - deterministic. Needs
+                                            myr_decode_attention_ws_bytes(B, H, cache_len) bytes, 16-byte aligned, ZEROED once; the
+                                            kernel leaves its counters at zero. NULL: one CTA walks the whole cache of a (row, head). */
 } myr_decode_attn_args;
 int myr_decode_attention(const myr_decode_attn_args* args, void* stream);
+int64_t myr_decode_attention_ws_bytes(int32_t B, int32_t H, int32_t cache_len);
 
 /* ---- persistent decode-step kernel ----------------------------------------------------------------------------------
  * One launch = one greedy-decode step of the whole LLaMA stack for T <= 16 sequences (modeling_llama.py:466-716 with a

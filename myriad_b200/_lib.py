@@ -28,6 +28,7 @@ def lib():
         _lib.myr_launch_count.restype = ctypes.c_ulonglong
         _lib.myr_mega_plan_bytes.restype = ctypes.c_size_t
         _lib.myr_gemm_workspace_bytes.restype = ctypes.c_size_t
+        _lib.myr_decode_attention_ws_bytes.restype = ctypes.c_int64
     return _lib
 
 

@@ -211,23 +211,9 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
 // not share an SM with a full-ring weight-streaming CTA: it starts as the qkv projection's CTA on its SM exits, and the
 // o_proj CTA follows it (measured on B200: 2.47 ms per decode step against 2.57 ms with the register version co-resident
 // with both; a shallower o_proj ring that would fit next to it costs more than it gains).
-//
-// Long caches (the throughput sweep's S = 1024 / 2048, or many rows): the same kernel with the cache cut into chunks of kv_cap
-// keys, one CTA per (head, row, chunk) - a 128-key chunk is 64 KB of K / V in shared memory, so three chunks of different
-// (head, row)s share an SM and one's arithmetic hides behind the others' transfers. Each CTA computes the new token's q (the
-// chunk that owns the new token's slot also appends k / v), its chunk's scores, a local softmax (max m_c, sum l_c) and the
-// unnormalised P.V, and leaves (m_c, l_c, o_c[128]) in the workspace. The last CTA of a (head, row) to arrive (one atomic per
-// CTA) combines the chunks in chunk order: O = sum_c e^{m_c - M} o_c / sum_c e^{m_c - M} l_c - the same result whichever CTA
-// arrives last: deterministic, CUDA-graph replay == eager.
-constexpr int DA_CHUNK = 128;       // keys per chunk of the split variant
-constexpr int DA_PART = 2 + DA_DH;  // floats per partial result
-
 struct DecodeAttnTmaParams {
   DecodeAttnParams a;
-  int kv_cap;     // rows per box (multiple of 8, <= 256) = keys per chunk
-  int n_split;    // chunks per (head, row): gridDim.z; 1 = the whole visible cache in one box
-  float* part;    // [B][H][n_split][DA_PART]   (n_split > 1)
-  int* counters;  // [B][H], zero on entry, left at zero
+  int kv_cap;  // rows per box (multiple of 8, <= 256)
 };
 
 __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __grid_constant__ CUtensorMap tmK,
@@ -242,11 +228,9 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
   float* s_scores = reinterpret_cast<float*>(tiles + 4 * tile_bytes);  // [kv_cap]
   __shared__ DecodeAttnSmem sm;
   __shared__ uint64_t bar;
-  __shared__ int s_last;
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int HD = p.H * DA_DH;
-  const int j_lo = blockIdx.z * pp.kv_cap;  // first cache slot of this CTA's chunk
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -262,22 +246,17 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
     }
   };
   stamp(0);
-  // step state is written by the greedy-update kernel at the END of the previous decode step: safe ahead of the wait
-  // (slots and lengths below are LOCAL to the chunk: slot j of the tile = cache slot j_lo + j)
-  const int off_g = p.cache_off ? __ldcg(p.cache_off) : p.cache_off_host;
-  const int off = off_g - j_lo;
-  int kvl = (p.kv_len ? __ldcg(p.kv_len + b) : off_g + 1);
-  if (kvl > p.Smax) kvl = p.Smax;
-  kvl -= j_lo;
-  if (kvl > pp.kv_cap) kvl = pp.kv_cap;
-  if (kvl < 0) kvl = 0;  // this chunk lies beyond the visible cache: nothing to load or compute, only the arrival below
-  if (tid == 0 && kvl > 0) {
+  if (tid == 0) {
     mbar_arrive_expect_tx(&bar, (uint32_t)(4 * tile_bytes));
     for (int hf = 0; hf < 2; ++hf) {
-      tma_load_4d(sK + hf * tile_bytes, &tmK, &bar, hf * 64, h, j_lo, b);
-      tma_load_4d(sV + hf * tile_bytes, &tmV, &bar, hf * 64, h, j_lo, b);
+      tma_load_4d(sK + hf * tile_bytes, &tmK, &bar, hf * 64, h, 0, b);
+      tma_load_4d(sV + hf * tile_bytes, &tmV, &bar, hf * 64, h, 0, b);
     }
   }
+  // step state is written by the greedy-update kernel at the END of the previous decode step: safe ahead of the wait
+  const int off = p.cache_off ? __ldcg(p.cache_off) : p.cache_off_host;
+  int kvl = p.kv_len ? __ldcg(p.kv_len + b) : off + 1;
+  if (kvl > pp.kv_cap) kvl = pp.kv_cap;
   __half* kbase = p.kcache + (size_t)b * p.c_bs + h * DA_DH;
   __half* vbase = p.vcache + (size_t)b * p.c_bs + h * DA_DH;
   const int pos = __ldcg(p.pos + b);
@@ -325,14 +304,14 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
     const __half vo1 = __float2half_rn(v1), vo2 = __float2half_rn(v2);
     sm.k[j] = ko1; sm.k[half + j] = ko2;
     sm.v[j] = vo1; sm.v[half + j] = vo2;
-    if (off >= 0 && off < pp.kv_cap && off_g < p.Smax) {  // the chunk that owns the new token's slot appends it
-      __half* kd = kbase + (size_t)off_g * p.c_ts;
-      __half* vd = vbase + (size_t)off_g * p.c_ts;
+    if (off >= 0 && off < p.Smax) {
+      __half* kd = kbase + (size_t)off * p.c_ts;
+      __half* vd = vbase + (size_t)off * p.c_ts;
       kd[j] = ko1; kd[half + j] = ko2;
       vd[j] = vo1; vd[half + j] = vo2;
     }
   }
-  if (kvl > 0) mbar_wait(&bar, 0);  // K / V tiles have landed (requested before the wait)
+  mbar_wait(&bar, 0);  // K / V tiles have landed (requested before the wait)
   __syncthreads();
   stamp(2);
 
@@ -391,7 +370,7 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) sm.acc[warp][lane * 4 + i] = acc[i];
-  if (p.next_layer_stride && pp.n_split == 1) {
+  if (p.next_layer_stride) {
     // ask L2 for the next layer's slice of the cache now (its attention runs ~80 us from now; weights are loaded
     // evict-first, so the lines survive until then)
     const __half* kn = kbase + p.next_layer_stride;
@@ -403,53 +382,25 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
     }
   }
   __syncthreads();
-  const float o_c = (sm.acc[0][tid] + sm.acc[1][tid]) + (sm.acc[2][tid] + sm.acc[3][tid]);
-  if (pp.n_split == 1) {
-    p.out[(size_t)b * p.ldo + h * DA_DH + tid] = __float2half_rn(l > 0.f ? o_c / l : 0.f);
-    stamp(5);
-    return;
-  }
-  // ---- split: leave this chunk's (max, sum, unnormalised P.V); the last chunk of the (head, row) to arrive combines them
-  float* base = pp.part + (size_t)(b * p.H + h) * pp.n_split * DA_PART;
-  if (kvl > 0) {
-    float* mine = base + blockIdx.z * DA_PART;
-    mine[2 + tid] = o_c;
-    if (tid == 0) {
-      mine[0] = m;
-      mine[1] = l;
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    int* ctr = pp.counters + b * p.H + h;
-    const int old = atomicAdd(ctr, 1);
-    s_last = (old == pp.n_split - 1);
-    if (s_last) *ctr = 0;  // every chunk has arrived: leave the counter clean for the next launch / graph replay
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    int kv_all = p.kv_len ? __ldcg(p.kv_len + b) : off_g + 1;
-    if (kv_all > p.Smax) kv_all = p.Smax;
-    const int ns = (kv_all + pp.kv_cap - 1) / pp.kv_cap;  // chunks that hold visible keys (the others wrote nothing)
-    float M = -INFINITY;
-    for (int cc = 0; cc < ns; ++cc) M = fmaxf(M, __ldcg(base + cc * DA_PART));
-    float L = 0.f, O = 0.f;
-    for (int cc = 0; cc < ns; ++cc) {
-      const float w = __expf(__ldcg(base + cc * DA_PART) - M);
-      L = fmaf(w, __ldcg(base + cc * DA_PART + 1), L);
-      O = fmaf(w, __ldcg(base + cc * DA_PART + 2 + tid), O);
-    }
-    p.out[(size_t)b * p.ldo + h * DA_DH + tid] = __float2half_rn(L > 0.f ? O / L : 0.f);
+  {
+    const float o = (sm.acc[0][tid] + sm.acc[1][tid]) + (sm.acc[2][tid] + sm.acc[3][tid]);
+    p.out[(size_t)b * p.ldo + h * DA_DH + tid] = __float2half_rn(l > 0.f ? o / l : 0.f);
   }
   stamp(5);
 }
 
-
 }  // namespace myr
 
 using namespace myr;
+
+// decode_attn_stream.cu: persistent flat-work-list kernel for long caches
+size_t myr_decode_attn_stream_ws(int B, int H, int cache_len);
+int myr_decode_attn_stream_launch(const DecodeAttnParams& p, void* ws, size_t ws_bytes, const void* kcache, const void* vcache,
+                                  cudaStream_t stream);
+
+extern "C" int64_t myr_decode_attention_ws_bytes(int32_t B, int32_t H, int32_t cache_len) {
+  return (int64_t)myr_decode_attn_stream_ws(B, H, cache_len);
+}
 
 extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -482,9 +433,6 @@ extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_
     pp.a = p;
     pp.a.trace = (a->B * a->H <= 148) ? next_trace_slot() : nullptr;
     pp.kv_cap = (a->kv_cap + 7) / 8 * 8;
-    pp.n_split = 1;
-    pp.part = nullptr;
-    pp.counters = nullptr;
     CUtensorMap tmK, tmV;
     {
       const void* ptrs[2] = {a->kcache, a->vcache};
@@ -508,43 +456,10 @@ extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_
     MYR_CHECK_LAUNCH();
     return MYR_OK;
   }
-  // long caches: one CTA per 128-key chunk (flash-decoding), partials combined by the last CTA of each (head, row)
-  {
-    const int n_split = (a->cache_len + DA_CHUNK - 1) / DA_CHUNK;
-    const size_t ctr_bytes = ((size_t)a->B * a->H * 4 + 15) & ~size_t(15);
-    const size_t need = ctr_bytes + (size_t)a->B * a->H * n_split * DA_PART * 4;
-    if (a->split_ws != nullptr && a->kv_cap == 0 && a->cache_len > 2 * DA_CHUNK && n_split <= 65535 && a->split_ws_bytes >= need &&
-        (reinterpret_cast<uintptr_t>(a->split_ws) & 15) == 0) {
-      DecodeAttnTmaParams pp;
-      pp.a = p;
-      pp.kv_cap = DA_CHUNK;
-      pp.n_split = n_split;
-      pp.counters = reinterpret_cast<int*>(a->split_ws);
-      pp.part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->split_ws) + ctr_bytes);
-      CUtensorMap tmK, tmV;
-      {
-        const void* ptrs[2] = {a->kcache, a->vcache};
-        CUtensorMap* maps[2] = {&tmK, &tmV};
-        for (int i = 0; i < 2; ++i) {
-          const uint64_t dims[4] = {(uint64_t)DA_DH, (uint64_t)a->H, (uint64_t)a->cache_len, (uint64_t)a->B};
-          const uint64_t strides[3] = {(uint64_t)DA_DH * 2, (uint64_t)a->cache_token_stride * 2, (uint64_t)a->cache_batch_stride * 2};
-          const uint32_t box[4] = {64, 1, (uint32_t)DA_CHUNK, 1};
-          const int rc = make_tmap_f16(maps[i], ptrs[i], 4, dims, strides, box);
-          if (rc) return rc;
-        }
-      }
-      const size_t smem = (size_t)DA_CHUNK * (4 * 128 + 4) + 1024;
-      static bool attr3 = false;
-      if (!attr3) {
-        MYR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        MYR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr3 = true;
-      }
-      MYR_CHECK_CUDA(launch_kernel(decode_attn_tma_kernel, dim3(a->H, a->B, n_split), dim3(DA_THREADS), smem, stream, true, tmK, tmV, pp));
-      MYR_CHECK_LAUNCH();
-      return MYR_OK;
-    }
-  }
+  // long caches: persistent CTAs over the flat list of 128-key chunks, partial results combined in order (decode_attn_stream.cu)
+  if (a->split_ws != nullptr && a->kv_cap == 0 && a->cache_len > 256 && a->B <= 128 &&
+      (reinterpret_cast<uintptr_t>(a->split_ws) & 15) == 0)
+    return myr_decode_attn_stream_launch(p, a->split_ws, a->split_ws_bytes, a->kcache, a->vcache, stream);
   static bool attr_set = false;
   if (!attr_set) {
     // same L1 / shared-memory split as the weight-streaming kernels around it: an SM only hosts CTAs of two kernels at once

@@ -250,8 +250,8 @@ class DecodeAttnArgs(ctypes.Structure):
 
 
 def decode_attn_split_bytes(B, H, cache_len):
-    """Workspace (zero-initialised by the caller, once) of the long-cache decode attention: counters + per-chunk partials."""
-    return B * H * (4 + ((cache_len + 127) // 128) * 520) + 64
+    """Workspace (zero-initialised by the caller, once) of the long-cache decode attention: counters + partial results."""
+    return int(lib().myr_decode_attention_ws_bytes(B, H, cache_len)) + 64
 
 
 def decode_attention(qkv, B, H, dh, pos, cos, sin, kcache, vcache, kv_len, out, scale, cache_off=0, cache_off_dev=None, lora=None,
