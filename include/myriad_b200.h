@@ -328,6 +328,24 @@ int myr_conv3x3_dgrad(const void* dy, const void* w, void* din, int32_t B, int32
 int myr_col2im(const void* dcols, void* din, int32_t B, int32_t H, int32_t W, int32_t C, int32_t KH, int32_t KW, int32_t pad,
                void* stream);
 
+
+/* ---- vision expert heads (adrefexpert_v2.py:245-301); the ImageBind-Huge trunk (imagebind_model.py:486-504,
+ * transformer.py:104-170) runs on myr_patchify / myr_gemm_f16 / myr_norm / myr_attention_fwd ----------------------------------- */
+/* tokens[i].transpose(0,1)[:, 1:, :] (adrefexpert_v2.py:26-27,215-216): x fp32 [B, N, D] -> out fp16 [B, N-1, D] without the class
+ * token; normalize != 0: every row divided by max(|row|, 1e-8) (operand of F.cosine_similarity, :270). */
+int myr_expert_tap(const void* x, void* out16, int32_t B, int32_t N, int32_t D, int32_t normalize, void* stream);
+/* zero-shot logits :285-286: logits[b*P + p][k] = scale * tokens[b*P + p] . text[b][k] / |tokens[b*P + p]|; tokens fp32 (row stride
+ * ld), text fp32 [B, 2, C], logits fp32 [B*P, 2]. */
+int myr_expert_logits(const void* tokens, int64_t ld, const void* text, void* logits, int32_t B, int32_t P, int32_t C, float scale,
+                      void* stream);
+/* :287-301: logits fp32 [L, B, G*G, 2] -> maps fp32 [B, OUT*OUT] = mean over L of softmax(bilinear_align_corners(logits))[:, 1],
+ * masks fp32 [B, G*G] = mean over L of softmax(logits)[:, 1]. */
+int myr_expert_maps(const void* logits, void* maps, void* masks, int32_t L, int32_t B, int32_t G, int32_t OUT, void* stream);
+/* k-shot :270-272: acc[row] (+)= weight * max_r S[row][r]; S fp32 [rows, R] (row stride ld) = cosine similarities. */
+int myr_expert_rowmax(const void* S, int64_t ld, void* acc, int32_t rows, int32_t R, float weight, int32_t accumulate, void* stream);
+/* k-shot :274-278: sim fp32 [B, G*G] -> simmask [B, G*G] = 1 - sim, maps [B, OUT*OUT] = 1 - bilinear_align_corners(sim). */
+int myr_expert_sim_maps(const void* sim, void* maps, void* simmask, int32_t B, int32_t G, int32_t OUT, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -554,3 +554,26 @@ def conv3x3_dgrad(dy, w, din, B, H, W, Cin, Cout):
 
 def col2im(dcols, din, B, H, W, C, KH, KW, pad):
     check(lib().myr_col2im(_p(dcols), _p(din), B, H, W, C, KH, KW, pad, _stream()), "myr_col2im")
+
+
+# ---- vision expert heads (csrc/expert.cu; adrefexpert_v2.py:245-301)
+def expert_tap(x, out16, B, N, D, normalize=False):
+    check(lib().myr_expert_tap(_p(x), _p(out16), B, N, D, int(normalize), _stream()), "myr_expert_tap")
+
+
+def expert_logits(tokens, text, logits, B, P, C, scale=100.0):
+    assert tokens.dtype == torch.float32 and text.dtype == torch.float32 and logits.dtype == torch.float32
+    check(lib().myr_expert_logits(_p(tokens), _i64(tokens.stride(0)), _p(text), _p(logits), B, P, C, _f32(scale), _stream()),
+          "myr_expert_logits")
+
+
+def expert_maps(logits, maps, masks, L, B, G, OUT):
+    check(lib().myr_expert_maps(_p(logits), _p(maps), _p(masks), L, B, G, OUT, _stream()), "myr_expert_maps")
+
+
+def expert_rowmax(S, ld, acc, rows, R, weight, accumulate):
+    check(lib().myr_expert_rowmax(_p(S), _i64(ld), _p(acc), rows, R, _f32(weight), int(accumulate), _stream()), "myr_expert_rowmax")
+
+
+def expert_sim_maps(sim, maps, simmask, B, G, OUT):
+    check(lib().myr_expert_sim_maps(_p(sim), _p(maps), _p(simmask), B, G, OUT, _stream()), "myr_expert_sim_maps")
