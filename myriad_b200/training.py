@@ -284,36 +284,48 @@ class MyriadTrainer(MyriadEngine):
         return out32, out16
 
     # --------------------------------------------------------------------------------------- attention backward
+    ATTN_BWD_WS_BYTES = int(os.environ.get("MYR_ATTN_BWD_WS_MB", "1024")) << 20
+
     def _attn_bwd(self, q, k, v, dctx, dq, dk, dv, B, H, Sq, Skv, dh, scale, causal, kv_len):
         """q/k/v/dq/dk/dv: (tensor_view, token_stride, batch_stride) with head stride dh; dctx fp16 [B*Sq, H*dh].
         P is re-materialised: S = Q K^T (batched tcgen05 GEMM, fp32) -> masked softmax -> dV = P^T dO, dP = dO V^T,
-        dS = scale * P * (dP - rowsum(dP * P)), dQ = dS K, dK = dS^T Q."""
+        dS = scale * P * (dP - rowsum(dP * P)), dQ = dS K, dK = dS^T Q.
+        Heads are independent, so the S x S work buffers (8 bytes per score) are sized for a GROUP of heads that fits
+        ATTN_BWD_WS_BYTES and the group loop walks the heads: 164-token training sequences take one pass (27 MB), the sweep's
+        S = 2048 at batch 4 takes 5 passes of 7 heads (0.94 GB each) instead of one 4.3 GB allocation per layer."""
         dev = self.dev
         Sp = (Skv + 63) // 64 * 64
-        n = B * H * Sq
+        per_head = B * Sq * Sp * 8
+        hc = max(1, min(H, self.ATTN_BWD_WS_BYTES // max(1, per_head)))
+        n = B * hc * Sq
         S32 = torch.empty(n, Sp, device=dev, dtype=F32)
         P16 = torch.empty(n, Sp, device=dev, dtype=F16)
         dS16 = torch.empty(n, Sp, device=dev, dtype=F16)
-        obs = (H * Sq * Sp, Sq * Sp)
         (qt, q_ts, q_bs), (kt, k_ts, k_bs), (vt, v_ts, v_bs) = q, k, v
-        HD = H * dh
-        K.gemm(qt, kt, out=S32.reshape(-1), out_dtype=F32, T=Sq, F=Skv, K=dh, ldx=q_ts, ldw=k_ts, ldo=Sp,
-               batch=(B, H, (q_bs, dh), (k_bs, dh), obs))
-        K.softmax_rows(S32, P16, B, H, Sq, Skv, Sp, scale, causal, kv_len)
-        # dP = dO V^T (reuse S32)
-        K.gemm(dctx, vt, out=S32.reshape(-1), T=Sq, F=Skv, K=dh, ldx=HD, ldw=v_ts, ldo=Sp,
-               batch=(B, H, (Sq * HD, dh), (v_bs, dh), obs))
-        K.softmax_bwd_rows(P16, S32, dS16, n, Sp, scale)
         (dqt, dq_ts, dq_bs), (dkt, dk_ts, dk_bs), (dvt, dv_ts, dv_bs) = dq, dk, dv
-        # dV[key, d] = sum_q P[q, key] dO[q, d]
-        K.gemm(P16, dctx, out=dvt, x_mn_major=True, w_mn_major=True, T=Skv, F=dh, K=Sq, ldx=Sp, ldw=HD, ldo=dv_ts, bn_hint=64,
-               batch=(B, H, obs, (Sq * HD, dh), (dv_bs, dh)))
-        # dQ[q, d] = sum_key dS[q, key] K[key, d]
-        K.gemm(dS16, kt, out=dqt, w_mn_major=True, T=Sq, F=dh, K=Skv, ldx=Sp, ldw=k_ts, ldo=dq_ts,
-               batch=(B, H, obs, (k_bs, dh), (dq_bs, dh)))
-        # dK[key, d] = sum_q dS[q, key] Q[q, d]
-        K.gemm(dS16, qt, out=dkt, x_mn_major=True, w_mn_major=True, T=Skv, F=dh, K=Sq, ldx=Sp, ldw=q_ts, ldo=dk_ts, bn_hint=64,
-               batch=(B, H, obs, (q_bs, dh), (dk_bs, dh)))
+        HD = H * dh
+        for h0 in range(0, H, hc):
+            hn = min(hc, H - h0)
+            o = h0 * dh  # element offset of the group's first head inside a token row
+            qv, kv_, vv, dov = qt[..., o:], kt[..., o:], vt[..., o:], dctx[..., o:]  # views: only the data pointer moves
+            dqv, dkv, dvv = dqt[..., o:], dkt[..., o:], dvt[..., o:]
+            obs = (hn * Sq * Sp, Sq * Sp)
+            K.gemm(qv, kv_, out=S32.reshape(-1), out_dtype=F32, T=Sq, F=Skv, K=dh, ldx=q_ts, ldw=k_ts, ldo=Sp,
+                   batch=(B, hn, (q_bs, dh), (k_bs, dh), obs))
+            K.softmax_rows(S32, P16, B, hn, Sq, Skv, Sp, scale, causal, kv_len)
+            # dP = dO V^T (reuse S32)
+            K.gemm(dov, vv, out=S32.reshape(-1), T=Sq, F=Skv, K=dh, ldx=HD, ldw=v_ts, ldo=Sp,
+                   batch=(B, hn, (Sq * HD, dh), (v_bs, dh), obs))
+            K.softmax_bwd_rows(P16, S32, dS16, B * hn * Sq, Sp, scale)
+            # dV[key, d] = sum_q P[q, key] dO[q, d]
+            K.gemm(P16, dov, out=dvv, x_mn_major=True, w_mn_major=True, T=Skv, F=dh, K=Sq, ldx=Sp, ldw=HD, ldo=dv_ts, bn_hint=64,
+                   batch=(B, hn, obs, (Sq * HD, dh), (dv_bs, dh)))
+            # dQ[q, d] = sum_key dS[q, key] K[key, d]
+            K.gemm(dS16, kv_, out=dqv, w_mn_major=True, T=Sq, F=dh, K=Skv, ldx=Sp, ldw=k_ts, ldo=dq_ts,
+                   batch=(B, hn, obs, (k_bs, dh), (dq_bs, dh)))
+            # dK[key, d] = sum_q dS[q, key] Q[q, d]
+            K.gemm(dS16, qv, out=dkv, x_mn_major=True, w_mn_major=True, T=Skv, F=dh, K=Sq, ldx=Sp, ldw=q_ts, ldo=dk_ts, bn_hint=64,
+                   batch=(B, hn, obs, (q_bs, dh), (dk_bs, dh)))
 
     # --------------------------------------------------------------------------------------------- conv stacks
     def _conv_trunk_train(self, maps, W):

@@ -169,6 +169,12 @@ def test_attention_bwd(cfg):
     eq, ek, ev = rel(dq, q.grad.reshape(-1, HD)), rel(dk, k.grad.reshape(-1, HD)), rel(dv, v.grad.reshape(-1, HD))
     print("attention bwd %s: dq %.2e dk %.2e dv %.2e" % (cfg, eq, ek, ev))
     assert max(eq, ek, ev) < TOL_UNIT
+    # bounded work buffers: one head per pass (the S = 2048 sweep shape takes 5 passes) must give the same bits
+    tr.ATTN_BWD_WS_BYTES = B * Sq * ((Skv + 63) // 64 * 64) * 8
+    dq2, dk2, dv2 = torch.zeros_like(qd), torch.zeros_like(kd), torch.zeros_like(vd)
+    tr._attn_bwd((qd, HD, Sq * HD), (kd, HD, Skv * HD), (vd, HD, Skv * HD), dod, (dq2, HD, Sq * HD), (dk2, HD, Skv * HD),
+                 (dv2, HD, Skv * HD), B, H, Sq, Skv, dh, scale, cfg["causal"], kv_len)
+    assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
 
 
 def test_conv_trunk_fwd_bwd(K, O):
