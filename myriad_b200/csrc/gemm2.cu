@@ -44,6 +44,7 @@ struct Gemm2Params {
   int* flags;          // [tile][rank in pair]: splits of a tile that have written their contribution (ordered => deterministic)
   int dbg;             // timing ablations (MYR_G2_DBG; results are wrong): 1 no MMAs, 2 no N-side TMA, 4 no A TMA, 8 MMAs with N = 16
   int pf_dist;         // L2 prefetch distance of the weight operand in k-blocks (0 = off)
+  int ka;              // 64-wide k-atoms per ring stage (1: 2-D tensor maps; 2 / 4: 3-D maps (64 k, rows, atoms), K % 64 == 0, P == 1)
   uint32_t idesc;
   long long* trace;  // debug (myr_gemm_set_trace): per CTA 6 x %globaltimer ns
   Epilogue ep;
@@ -117,7 +118,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       uint16_t mask_rank = 0;
       for (int q = 0; q < p.P; ++q) mask_rank |= (uint16_t)(1u << (2 * q + r));
-      const uint32_t tx_pair = 2u * (((p.dbg & 4) ? 0u : (uint32_t)G2_A_BYTES) + ((p.dbg & 2) ? 0u : b_half_bytes));  // bytes landing in both CTAs of a pair per stage
+      const uint32_t tx_pair = 2u * (uint32_t)p.ka * (((p.dbg & 4) ? 0u : (uint32_t)G2_A_BYTES) + ((p.dbg & 2) ? 0u : b_half_bytes));  // bytes landing in both CTAs of a pair per stage
       int stage = 0;
       uint32_t phase = 0;
       pdl_wait();
@@ -147,12 +148,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if ((p.dbg & 16) && p.trace && blockIdx.x < 2 && u == cluster_id && kb < 64) p.trace[888 + (blockIdx.x ? 128 : 0) + kb] = gtime_ns();
           if (r == 0) mbar_arrive_expect_tx(&full[stage], tx_pair);
           uint8_t* sa = smem + stage * p.stage_bytes;
-          if (p.dbg & 4) {
+          if (p.ka > 1) {
+            // one copy per operand and stage brings ka k-atoms (a copy costs the issuing thread the same whatever its size)
+            if (!(p.dbg & 4)) tma_load_3d_pair(sa, &tmA, &full[stage], 0, a_row0, kb * p.ka);
+            if (!(p.dbg & 2)) tma_load_3d_pair(sa + p.ka * G2_A_BYTES, &tmB, &full[stage], 0, b_row0, kb * p.ka);
+          } else if (p.dbg & 4) {
           } else if (p.P > 1)
             tma_load_2d_pair_multicast(sa + pr * a_slice_rows * (G2_BK * 2), &tmA, &full[stage], kb * G2_BK, a_row0, mask_rank);
           else
             tma_load_2d_pair(sa, &tmA, &full[stage], kb * G2_BK, a_row0);
-          if (!(p.dbg & 2)) tma_load_2d_pair(sa + G2_A_BYTES, &tmB, &full[stage], kb * G2_BK, b_row0);
+          if (p.ka == 1 && !(p.dbg & 2)) tma_load_2d_pair(sa + G2_A_BYTES, &tmB, &full[stage], kb * G2_BK, b_row0);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
@@ -180,12 +185,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           if ((p.dbg & 16) && p.trace && blockIdx.x == 0 && u == cluster_id && kb < 64) p.trace[888 + 64 + kb] = gtime_ns();
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
-          const uint32_t sb = sa + G2_A_BYTES;
+          const uint32_t sb = sa + p.ka * G2_A_BYTES;
+          for (int at = 0; at < p.ka; ++at) {  // k-atom at of the stage: [atom][row][128 B] per operand
+            const uint32_t sa_at = sa + at * G2_A_BYTES, sb_at = sb + at * b_half_bytes;
 #pragma unroll
-          for (int kk = 0; kk < G2_BK / 16; ++kk) {
-            const uint64_t da = make_smem_desc(sa + kk * 32, 16, 1024);
-            const uint64_t db = make_smem_desc(sb + kk * 32, 16, 1024);
-            if (!(p.dbg & 1)) tc_mma_f16_pair(d_tmem, da, db, p.idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < G2_BK / 16; ++kk) {
+              const uint64_t da = make_smem_desc(sa_at + kk * 32, 16, 1024);
+              const uint64_t db = make_smem_desc(sb_at + kk * 32, 16, 1024);
+              if (!(p.dbg & 1)) tc_mma_f16_pair(d_tmem, da, db, p.idesc, (kb > kb0 || at > 0 || kk > 0) ? 1u : 0u);
+            }
           }
           tc_commit_pair(&empty[stage], mask_all);  // frees this stage in every CTA that multicasts into the pair
           if (++stage == p.num_stages) {
@@ -414,7 +422,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // host side
 // ---------------------------------------------------------------------------------------------------
 struct Plan2 {
-  int row_mode, BN, P, S, n_mt, n_nt, n_ng, n_units, n_clusters, num_stages, stage_bytes;
+  int row_mode, BN, P, S, n_mt, n_nt, n_ng, n_units, n_clusters, num_stages, stage_bytes, ka, swiglu;
   double cost;
 };
 
@@ -462,16 +470,21 @@ static void g2_fill(Plan2& pl, int T, int F, int K) {
   pl.n_nt = ceil_div(rows_b, pl.BN);
   pl.n_ng = ceil_div(pl.n_nt, pl.P);
   pl.n_units = pl.n_mt * pl.n_ng * pl.S;
-  pl.stage_bytes = G2_A_BYTES + (pl.BN / 2) * G2_BK * 2;
-  int st = G2_SMEM_TILE_BUDGET / pl.stage_bytes;
+  // ring stage = ka k-atoms of 64: a TMA copy costs its issuing thread ~0.15 us whatever its size, and at one atom per stage
+  // (two copies per 64 k) the main loop ran at the copy-issue rate, not at the tensor or the memory rate (profiles/r2_gemm2_sweep.md)
+  pl.ka = (K % G2_BK == 0 && pl.P == 1) ? env_int("MYR_G2_KA", 2) : 1;
+  if (pl.ka < 1 || pl.ka > 4) pl.ka = 1;
+  pl.stage_bytes = pl.ka * (G2_A_BYTES + (pl.BN / 2) * G2_BK * 2);
+  // the SwiGLU hand-over buffer is only there for that epilogue: the other launches give its 8 KB (and the slack) to the ring
+  const int budget = pl.swiglu ? G2_SMEM_TILE_BUDGET : (227 * 1024 - 1024 - 256 - 512);
+  int st = budget / pl.stage_bytes;
   pl.num_stages = st > G2_MAX_STAGES ? G2_MAX_STAGES : st;
   const int f_st = env_int("MYR_G2_STAGES", 0);
   if (f_st > 0 && f_st < pl.num_stages) pl.num_stages = f_st;
-  (void)K;
 }
 
 static size_t g2_smem_bytes(const Plan2& pl) {
-  return (size_t)pl.num_stages * pl.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + G2_SWIGLU_STAGE_BYTES;
+  return (size_t)pl.num_stages * pl.stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + (pl.swiglu ? G2_SWIGLU_STAGE_BYTES : 0);
 }
 
 // split-K adds partial sums in place, in split order: only for fp32 out = fp32 residual + X W^T (o_proj / down_proj / ViT
@@ -510,6 +523,7 @@ static Plan2 g2_plan(const myr_gemm_args* a) {
           if (S > 1 && (!split_ok || mode != 0 || (S - 1) * ceil_div(kb, S) >= kb || kb / S < 8)) continue;
           Plan2 pl;
           pl.row_mode = mode;
+          pl.swiglu = swiglu ? 1 : 0;
           pl.BN = bn;
           pl.P = P;
           pl.S = S;
@@ -573,24 +587,37 @@ int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled) {
     uint32_t box[2];
     dims[0] = (uint64_t)a->K; dims[1] = (uint64_t)rows_a; box[0] = G2_BK; box[1] = (uint32_t)(G2_A_ROWS / pl.P);
     strides[0] = (uint64_t)lda * 2;
-    int rc = make_tmap_f16(&tmA, pa, 2, dims, strides, box);
-    if (rc) return rc;
-    dims[1] = (uint64_t)rows_b; box[1] = (uint32_t)(pl.BN / 2);
-    strides[0] = (uint64_t)ldb * 2;
-    rc = make_tmap_f16(&tmB, pb, 2, dims, strides, box);
-    if (rc) return rc;
+    int rc = MYR_OK;
+    if (pl.ka == 1) {
+      rc = make_tmap_f16(&tmA, pa, 2, dims, strides, box);
+      if (rc) return rc;
+      dims[1] = (uint64_t)rows_b; box[1] = (uint32_t)(pl.BN / 2);
+      strides[0] = (uint64_t)ldb * 2;
+      rc = make_tmap_f16(&tmB, pb, 2, dims, strides, box);
+      if (rc) return rc;
+    } else {
+      // (64 k, rows, K / 64 atoms): a box of ka atoms lands as [atom][row][128 B], each atom a canonical 128-byte-swizzled tile
+      uint64_t d3[3] = {G2_BK, (uint64_t)rows_a, (uint64_t)(a->K / G2_BK)}, s3[2] = {(uint64_t)lda * 2, G2_BK * 2};
+      uint32_t b3[3] = {G2_BK, G2_A_ROWS, (uint32_t)pl.ka};
+      rc = make_tmap_f16(&tmA, pa, 3, d3, s3, b3);
+      if (rc) return rc;
+      d3[1] = (uint64_t)rows_b; s3[0] = (uint64_t)ldb * 2; b3[1] = (uint32_t)(pl.BN / 2);
+      rc = make_tmap_f16(&tmB, pb, 3, d3, s3, b3);
+      if (rc) return rc;
+    }
   }
   Gemm2Params p;
   p.T = a->T; p.F = a->F; p.K = a->K;
   p.row_mode = pl.row_mode; p.BN = pl.BN; p.P = pl.P;
-  p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.n_ng = pl.n_ng; p.kb_total = ceil_div(a->K, G2_BK); p.n_units = pl.n_units;
+  p.n_mt = pl.n_mt; p.n_nt = pl.n_nt; p.n_ng = pl.n_ng; p.kb_total = ceil_div(a->K, G2_BK * pl.ka); p.n_units = pl.n_units;
   p.num_stages = pl.num_stages; p.stage_bytes = pl.stage_bytes;
   p.dbg = env_int("MYR_G2_DBG", 0);
   p.idesc = make_idesc_f16(256, (p.dbg & 8) ? 16 : pl.BN, 0, 0);
   p.S = pl.S;
   p.kb_per = ceil_div(p.kb_total, pl.S);
   p.flags = reinterpret_cast<int*>(a->workspace);  // head of the workspace: zero on entry, left at zero (include/myriad_b200.h)
-  p.pf_dist = env_int("MYR_G2_PF", 0);  // measured: prefetching ahead of the ring costs 10-15 % on B200 (profiles/r2_gemm2_sweep.md)
+  p.ka = pl.ka;
+  p.pf_dist = pl.ka > 1 ? 0 : env_int("MYR_G2_PF", 0);  // measured: prefetching ahead of the ring costs 10-15 % on B200 (profiles/r2_gemm2_sweep.md)
   p.trace = next_trace_slot();
   p.ep.bias = reinterpret_cast<const __half*>(a->bias);
   p.ep.act = a->act; p.ep.round_acc = a->round_acc;

@@ -276,6 +276,13 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUte
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
 }
+// 3-D variant: a box of (64 k, rows, k-atoms) lands as [k-atom][row][128 B]
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // same, delivered to the same CTA-relative offset of every CTA in cta_mask; each delivery completes on the leader of the
 // receiving CTA's pair
 __device__ __forceinline__ void tma_load_2d_pair_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,

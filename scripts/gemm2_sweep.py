@@ -106,11 +106,13 @@ def run_group(name):
         g.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / iters
+        ms = 1e9
+        for _ in range(5):  # best of 5 replays (a single replay varies by +-10 % with the clock state)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = min(ms, e0.elapsed_time(e1) / iters)
         # one traced launch: set-up done / first MMA wave / accumulator ready / epilogue done, relative to the earliest CTA
         import ctypes
         tr = torch.zeros(148 * 6 * 2, dtype=torch.int64, device=dev)
