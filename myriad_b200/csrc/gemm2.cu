@@ -66,7 +66,8 @@ __device__ __forceinline__ void g2_unit(const Gemm2Params& p, int u, int& mt, in
 __device__ __forceinline__ void g2_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __global__ void __launch_bounds__(G2_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Params p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA2,
+             const Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tail = smem + p.num_stages * p.stage_bytes;
@@ -149,8 +150,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (r == 0) mbar_arrive_expect_tx(&full[stage], tx_pair);
           uint8_t* sa = smem + stage * p.stage_bytes;
           if (p.ka > 1) {
-            // one copy per operand and stage brings ka k-atoms (a copy costs the issuing thread the same whatever its size)
-            if (!(p.dbg & 4)) tma_load_3d_pair(sa, &tmA, &full[stage], 0, a_row0, kb * p.ka);
+            // one copy per operand and stage brings ka k-atoms (a copy costs the issuing thread the same whatever its size);
+            // with P pairs per cluster this CTA's 1/P slice of the A rows goes to the same-rank CTA of every pair, one copy per atom
+            // (the slices of one atom must lie side by side: [atom][128 rows][128 B])
+            if (p.dbg & 4) {
+            } else if (p.P > 1) {
+              for (int at = 0; at < p.ka; ++at)
+                tma_load_2d_pair_multicast(sa + at * G2_A_BYTES + pr * a_slice_rows * (G2_BK * 2), &tmA2, &full[stage],
+                                           (kb * p.ka + at) * G2_BK, a_row0, mask_rank);
+            } else {
+              tma_load_3d_pair(sa, &tmA, &full[stage], 0, a_row0, kb * p.ka);
+            }
             if (!(p.dbg & 2)) tma_load_3d_pair(sa + p.ka * G2_A_BYTES, &tmB, &full[stage], 0, b_row0, kb * p.ka);
           } else if (p.dbg & 4) {
           } else if (p.P > 1)
@@ -472,7 +482,7 @@ static void g2_fill(Plan2& pl, int T, int F, int K) {
   pl.n_units = pl.n_mt * pl.n_ng * pl.S;
   // ring stage = ka k-atoms of 64: a TMA copy costs its issuing thread ~0.15 us whatever its size, and at one atom per stage
   // (two copies per 64 k) the main loop ran at the copy-issue rate, not at the tensor or the memory rate (profiles/r2_gemm2_sweep.md)
-  pl.ka = (K % G2_BK == 0 && pl.P == 1) ? env_int("MYR_G2_KA", 2) : 1;
+  pl.ka = (K % G2_BK == 0) ? env_int("MYR_G2_KA", 2) : 1;
   if (pl.ka < 1 || pl.ka > 4) pl.ka = 1;
   pl.stage_bytes = pl.ka * (G2_A_BYTES + (pl.BN / 2) * G2_BK * 2);
   // the SwiGLU hand-over buffer is only there for that epilogue: the other launches give its 8 KB (and the slack) to the ring
@@ -581,7 +591,8 @@ int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled) {
   const void* pb = pl.row_mode ? a->w : a->x;
   const int64_t lda = pl.row_mode ? a->ldx : a->ldw, ldb = pl.row_mode ? a->ldw : a->ldx;
   const int rows_a = pl.row_mode ? a->T : a->F, rows_b = pl.row_mode ? a->F : a->T;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA2;
+  memset(&tmA2, 0, sizeof(tmA2));
   {
     uint64_t dims[2], strides[1];
     uint32_t box[2];
@@ -601,6 +612,10 @@ int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled) {
       uint32_t b3[3] = {G2_BK, G2_A_ROWS, (uint32_t)pl.ka};
       rc = make_tmap_f16(&tmA, pa, 3, d3, s3, b3);
       if (rc) return rc;
+      if (pl.P > 1) {  // per-atom multicast slices of the A tile
+        rc = make_tmap_f16(&tmA2, pa, 2, dims, strides, box);
+        if (rc) return rc;
+      }
       d3[1] = (uint64_t)rows_b; s3[0] = (uint64_t)ldb * 2; b3[1] = (uint32_t)(pl.BN / 2);
       rc = make_tmap_f16(&tmB, pb, 3, d3, s3, b3);
       if (rc) return rc;
@@ -646,7 +661,7 @@ int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled) {
             pl.row_mode, pl.BN, pl.P, pl.S, pl.n_units, pl.n_clusters, pl.num_stages, pl.cost);
   const int grid = pl.n_clusters * 2 * pl.P;
   MYR_CHECK_CUDA(launch_kernel_cluster(gemm2_kernel, dim3((unsigned)grid), dim3(G2_THREADS), g2_smem_bytes(pl), stream, a->pdl != 0,
-                                       2 * pl.P, tmA, tmB, p));
+                                       2 * pl.P, tmA, tmB, tmA2, p));
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }

@@ -42,6 +42,13 @@ GROUPS = {
            [("ll_gu", 0, bn, 1, 1, {"NW": "2"}) for bn in (96, 128, 176, 256)] + [("big_gu", 0, bn, 1, 1, {"NW": "2"}) for bn in (128, 192, 256)],
     "abl": [("ll_gu", 0, bn, 1, 1, {"NW": "2", "MYR_G2_DBG": str(d)}) for bn in (176,) for d in (0, 1, 2, 4, 6, 8, 3, 5)],
     "tl": [("ll_gu", 0, 176, 1, 1, {"NW": "2", "MYR_G2_DBG": str(d)}) for d in (16, 17, 21)],
+    "few": [("vit_fc2", 0, 176, 1, 1), ("vit_fc2", 0, 176, 1, 2), ("vit_fc2", 0, 176, 1, 3), ("vit_fc2", 0, 128, 1, 1), ("vit_fc2", 0, 128, 1, 2),
+            ("vit_fc2", 0, 208, 1, 2), ("vit_proj", 0, 176, 1, 1), ("vit_proj", 0, 128, 1, 1), ("vit_proj", 0, 176, 1, 2),
+            ("ll_o", 0, 176, 1, 1), ("ll_o", 0, 144, 1, 1), ("ll_o", 0, 176, 1, 2), ("ll_down", 0, 176, 1, 1), ("ll_down", 0, 176, 1, 2),
+            ("ll_down", 0, 144, 1, 1), ("ll_down", 0, 144, 1, 2), ("vit_qkv", 0, 144, 1, 1), ("vit_qkv", 0, 176, 1, 1), ("vit_qkv", 0, 208, 1, 1),
+            ("vit_fc1", 0, 208, 1, 1), ("qf_kv", 0, 208, 1, 1)],
+    "mc": [(sh, 0, bn, P, 1) for sh, bn in (("big_gu", 256), ("big_down", 256), ("ll_gu", 176), ("ll_qkv", 176), ("vit_fc1", 176), ("tr_gu", 224), ("qf_kv", 208))
+           for P in (1, 2, 4)],
     "m1": [("vit_fc1", 1, 256, 1, 1), ("ll_gu", 1, 256, 1, 1), ("big_gu", 1, 256, 1, 1), ("big_down", 1, 256, 1, 1)],
 }
 
