@@ -104,6 +104,10 @@ int32_t myr_set_gemv(int32_t enabled);
  * (the rest handed out in groups through the atomic counter), counter used (0/1), ring stages, 1024-k stages per group,
  * bytes of shared memory besides the ring }. */
 int myr_gemv_plan(int32_t F, int32_t K, int32_t act, int32_t sms, int32_t have_counter, int32_t* out8);
+/* The same for the multi-token streaming kernel (csrc/gemv_mt.cu, 5 <= T <= 32: weights AND tokens go through one TMA ring, row
+ * groups of up to 32 output rows / 16 SwiGLU pairs): out6 = { 8-token slices NT = ceil(T / 8), units of 8 rows (8 pairs), units per
+ * row group, CTAs, units [0, u_static) split evenly by CTA index, ring stages of 512 k }. */
+int myr_gemv_mt_plan(int32_t T, int32_t F, int32_t K, int32_t act, int32_t sms, int32_t have_counter, int32_t* out6);
 size_t myr_gemm_workspace_bytes(int32_t T, int32_t F, int32_t K);
 int myr_gemm_f16(const myr_gemm_args* args, void* stream);
 /* Profiling aid: while set, every GEMM launch writes 148 x 6 %globaltimer stamps (CTA start, predecessor released, last MMA

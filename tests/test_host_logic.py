@@ -139,3 +139,38 @@ def test_gemv_work_split_covers_every_unit_once(F, K, act, have_counter):
         assert use_counter == 1 and n_units - u_static >= n_units // 4  # the large decode projections use the pool
     if (F, K) in ((4096, 4096), (4096, 11008)):
         assert use_counter == 0  # o_proj / down_proj: fewer than two row groups per CTA, even split only
+
+
+@pytest.mark.parametrize("T", [5, 8, 16, 17, 32])
+@pytest.mark.parametrize("F,K,act", [(4096, 4096, 0), (12304, 4096, 0), (4096, 11008, 0), (22016, 4096, 3), (32000, 4096, 0), (1100, 640, 0)])
+def test_gemv_mt_work_split_covers_every_unit_once(T, F, K, act):
+    """csrc/gemv_mt.cu (5 <= T <= 32): the producer's work list re-walked on the host from myr_gemv_mt_plan: every 8-row unit (SwiGLU:
+    8 gate / up pairs) is requested exactly once, a SwiGLU group of two units starts at an even unit (its 16 pairs stay inside one
+    64-row block of the interleaved weight), and ring + reduction buffer fit the shared-memory budget."""
+    import ctypes
+
+    from myriad_b200._lib import lib
+    out = (ctypes.c_int32 * 6)()
+    assert lib().myr_gemv_mt_plan(T, F, K, act, 148, 1, out) == 0
+    nt, n_units, gsz, grid, u_static, stages = list(out)
+    swiglu = act == 3
+    assert nt == -(-T // 8) and n_units == (F // 16 if swiglu else -(-F // 8)) and gsz == (2 if swiglu else 4)
+    assert 1 <= grid <= 148 and 0 <= u_static <= n_units and u_static % gsz == 0 or u_static == n_units
+    stage_bytes = 32768 + nt * 8192
+    assert 2 <= stages <= 6 and stages * stage_bytes + nt * 8192 + 2048 <= 227 * 1024
+    seen = [0] * n_units
+    for cta in range(grid):
+        u, s1 = cta * u_static // grid, (cta + 1) * u_static // grid
+        while u < s1:
+            nu = 1 if (swiglu and u % 2) else min(gsz, s1 - u)
+            assert not (swiglu and nu == 2 and u % 2)
+            for i in range(nu):
+                seen[u + i] += 1
+            u += nu
+    u = u_static
+    while u < n_units:  # pool groups start at multiples of gsz from u_static
+        nu = min(gsz, n_units - u)
+        for i in range(nu):
+            seen[u + i] += 1
+        u += gsz
+    assert seen == [1] * n_units
