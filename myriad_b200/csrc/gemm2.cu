@@ -529,7 +529,11 @@ static Plan2 g2_plan(const myr_gemm_args* a) {
       for (int P = 1; P <= 4; P *= 2) {
         if (f_p > 0 ? P != f_p : P != 1) continue;  // multicast across pairs measured no gain on B200 (L2 already merges)
         for (int S = 1; S <= 4; ++S) {
-          if (f_s > 0 ? S != f_s : S != 1) continue;  // ordered split-K serialises the epilogues of a tile's splits: measured a loss
+          // ordered split-K serialises the epilogues of a tile's splits: measured a loss, except where one split per tile leaves
+          // at least half of the CTA pairs idle and K is long (ViT fc2 at batch 4: 36 tiles x K = 6144 -> 33 us against 39 us)
+          const int base_units = ceil_div(mode ? T : F, 256) * ceil_div(ceil_div(mode ? F : T, bn), P);
+          const bool two_way = S == 2 && split_ok && mode == 0 && 2 * base_units <= sm_count() / 2 && kb >= 64;
+          if (f_s > 0 ? S != f_s : (S != 1 && !two_way)) continue;
           if (S > 1 && (!split_ok || mode != 0 || (S - 1) * ceil_div(kb, S) >= kb || kb / S < 8)) continue;
           Plan2 pl;
           pl.row_mode = mode;

@@ -19,5 +19,10 @@ done
 # one decode-graph replay (greedy_decode captures the step, then replays it) under memcheck
 MYR_SANITIZE=1 timeout ${T_SAN:-900} $SAN --tool memcheck --print-limit 20 --error-exitcode 86 \
     python -m pytest tests/test_engine_gpu.py -m gpu -q -x -k "llama_tiny_logits_and_greedy" > gpurun_out/sanitize_decode_graph.log 2>&1
-echo "memcheck decode graph: exit $? | $(grep -E 'ERROR SUMMARY' gpurun_out/sanitize_decode_graph.log | tail -1) | $(grep -E 'passed|failed' gpurun_out/sanitize_decode_graph.log | tail -1)" >> gpurun_out/sanitize_summary.txt
+rc_graph=$?
+# the vision-expert heads (csrc/expert.cu) and its trunk on the tiny configuration
+MYR_SANITIZE=1 timeout ${T_SAN:-900} $SAN --tool memcheck --print-limit 20 --error-exitcode 86 \
+    python -m pytest tests/test_expert_gpu.py -m gpu -q -x -k "not full_width" > gpurun_out/sanitize_expert.log 2>&1
+echo "memcheck vision expert: exit $? | $(grep -E 'ERROR SUMMARY' gpurun_out/sanitize_expert.log | tail -1) | $(grep -E 'passed|failed' gpurun_out/sanitize_expert.log | tail -1)" >> gpurun_out/sanitize_summary.txt
+echo "memcheck decode graph: exit $rc_graph | $(grep -E 'ERROR SUMMARY' gpurun_out/sanitize_decode_graph.log | tail -1) | $(grep -E 'passed|failed' gpurun_out/sanitize_decode_graph.log | tail -1)" >> gpurun_out/sanitize_summary.txt
 cat gpurun_out/sanitize_summary.txt
