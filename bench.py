@@ -237,6 +237,12 @@ def run_ours(args):
             del es
         except Exception as e:
             eager = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    expert = None
+    if rank == 0 and world == 1 and not args.no_expert:
+        try:
+            expert = run_expert_leg(dev, peaks)
+        except Exception as e:
+            expert = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if rank == 0:
         cfg = {"workload": "myriad_generate_b4", "model": "Myriad: EVA-ViT-g + Q-Former(81q) + Vicuna-7B LoRA r=8",
                "batch_per_gpu": BATCH, "global_batch": BATCH * world, "prompt_tokens": 32, "prefill_len": 131,
@@ -255,12 +261,48 @@ def run_ours(args):
                     "api": "registry.get_model_class('myriad')(...).generate(samples) with pinned host tensors and question strings"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
             "new_tokens_per_s": ntok / (ms / 1e3) * world, "weights_load_s": round(t_load, 1),
-            "train": train,
+            "train": train, "vision_expert": expert,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_expert_leg(dev, peaks):
+    """SURVEY.md §8 (f2), context next to the headline: the vision expert (adrefexpert_v2.py:245-301) at the benchmark batch - ImageBind-Huge
+    vision trunk (32 blocks x 1280, four taps) + zero-shot and 1-shot map heads, the two calls Myriad makes per batch (myriad.py:342-343) with
+    one trunk pass over the query images and the reference tokens cached. Device-resident inputs, CUDA events, 5 repetitions."""
+    import torch
+
+    from myriad_b200 import expert as X
+    from myriad_b200 import synthetic as syn
+    d = X.ExpertDims()
+    sd = {k: syn.synth("vision_expert." + k, shape, std, 0, device=dev, mean=mean) for k, shape, std, mean in X.expert_state_dict_spec(d)}
+    eng = X.VisionExpertEngine(sd, d, device=dev)
+    del sd
+    image, _ = syn.make_inputs(BATCH, seed=99, device="cpu")
+    refs, _ = syn.make_inputs(BATCH, seed=98, device="cpu")
+    image, refs = image.to(dev), refs.to(dev)
+    text = X.make_text_features(BATCH, d).to(dev)
+    refs_n = eng.encode_refs(refs, BATCH)
+    for _ in range(2):
+        eng.both(image, text, refs_n=refs_n)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 5
+    e0.record()
+    for _ in range(n):
+        (zm, _), (km, _) = eng.both(image, text, refs_n=refs_n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    T, D = BATCH * d.tokens, d.dim
+    flop = (max(d.out_layers) + 1) * (2.0 * T * D * (3 * D + D + 2 * d.mlp_hidden) + 4.0 * BATCH * d.heads * d.tokens * d.tokens * d.head_dim)
+    tf = flop / (ms / 1e3) / 1e12
+    return {"what": "adrefexpert zero-shot + 1-shot maps for %d images: ImageBind-Huge trunk (one pass) + both heads, reference tokens cached" % BATCH,
+            "ms_per_batch": ms, "images_per_s": BATCH / (ms / 1e3), "trunk_tflops": tf, "frac_of_tensor_peak": tf / peaks["tensor"],
+            "maps_finite": bool(torch.isfinite(zm).all() and torch.isfinite(km).all())}
 
 
 def run_train_leg(args, dims, dev, world, rank, barrier):
@@ -595,6 +637,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train tokens/s)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager fp16 GPU baseline of the same workload")
+    ap.add_argument("--no-expert", action="store_true", help="skip the vision-expert context measurement")
     ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: batch x sequence throughput sweep instead of the headline line")
     ap.add_argument("--sweep-batches", default="1,4,16,32")
     ap.add_argument("--sweep-seqs", default="256,1024,2048")

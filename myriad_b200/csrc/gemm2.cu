@@ -587,7 +587,11 @@ int gemm2_launch(const myr_gemm_args* a, cudaStream_t stream, int* handled) {
   // ... and so is a launch whose last wave of tiles would leave most CTA pairs idle (ViT qkv at batch 4: 102 tiles = 1.38 waves)
   const int waves = ceil_div(pl.n_units, pl.n_clusters);
   const double wave_eff = (double)pl.n_units / ((double)waves * pl.n_clusters);
-  if ((pl.n_units < env_int("MYR_G2_MIN_UNITS", 60) || wave_eff < 0.8) && env_int("MYR_G2_MODE", -1) < 0) {
+  // ... and so is a SHORT launch inside a sequence of other kernels: a pair-kernel launch (cluster of 2, all 512 TMEM columns, 200+ KB of
+  // shared memory) overlaps worse with its neighbours' tails than the single-CTA kernel; measured in situ, the ViT qkv GEMM (12 GFLOP, 136 tiles)
+  // cost the 39-block encoder +1.3 ms on this kernel although it is 1.6 us faster back to back (profiles/r2_gemm2_sweep.md §5)
+  const double gflop = 2.0 * a->T * (double)a->F * a->K * 1e-9;
+  if ((pl.n_units < env_int("MYR_G2_MIN_UNITS", 60) || wave_eff < 0.8 || gflop < env_int("MYR_G2_MIN_GFLOP", 15)) && env_int("MYR_G2_MODE", -1) < 0) {
     *handled = 0;
     return MYR_OK;
   }
