@@ -108,15 +108,10 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
   auto score = [&](const uint4 (&kv)[DA_DH / 8], int j) {
     if (j < kvl) {
       const uint4* ks = reinterpret_cast<const uint4*>(sm.k);
-      float d = 0.f;
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < DA_DH / 8; ++i) {
-        float kf[8];
-        da_unpack8(j == off ? ks[i] : kv[i], kf);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d = fmaf(kf[e], sm.q[i * 8 + e], d);
-      }
-      s_scores[j] = d * p.scale;
+      for (int i = 0; i < DA_DH / 8; ++i) da_dot8(j == off ? ks[i] : kv[i], sm.q + i * 8, d);
+      s_scores[j] = da_dot_finish(d) * p.scale;
     }
   };
 #pragma unroll 1
@@ -317,17 +312,14 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
 
   // ---- phase 1: scores, one key per thread and pass; rows come from the swizzled tiles (the new token's from sm.k)
   for (int j = tid; j < kvl; j += DA_THREADS) {
-    float d = 0.f;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < DA_DH / 8; ++i) {
       const uint4 raw = (j == off) ? reinterpret_cast<const uint4*>(sm.k)[i]
                                    : *reinterpret_cast<const uint4*>(sK + (i >> 3) * tile_bytes + j * 128 + (((i & 7) ^ (j & 7)) << 4));
-      float kf[8];
-      da_unpack8(raw, kf);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) d = fmaf(kf[e], sm.q[i * 8 + e], d);
+      da_dot8(raw, sm.q + i * 8, d);
     }
-    s_scores[j] = d * p.scale;
+    s_scores[j] = da_dot_finish(d) * p.scale;
   }
   __syncthreads();
   stamp(3);
@@ -357,16 +349,30 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
   // ---- phase 2: O = P V. Warp w owns keys j = w (mod 4) in increasing order; lane l owns dims [4l, 4l + 4)
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const int v_half = lane >> 4, v_unit = (lane & 15) >> 1, v_sub = (lane & 1) * 8;
-  for (int j = warp; j < kvl; j += 4) {
-    const float pj = s_scores[j];
-    const uint2 raw = (j == off) ? *reinterpret_cast<const uint2*>(sm.v + lane * 4)
-                                 : *reinterpret_cast<const uint2*>(sV + v_half * tile_bytes + j * 128 + ((v_unit ^ (j & 7)) << 4) + v_sub);
-    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-    const float2 a = __half22float2(h2[0]), bb = __half22float2(h2[1]);
-    acc[0] = fmaf(pj, a.x, acc[0]);
-    acc[1] = fmaf(pj, a.y, acc[1]);
-    acc[2] = fmaf(pj, bb.x, acc[2]);
-    acc[3] = fmaf(pj, bb.y, acc[3]);
+  // four keys per step: their probability / value loads are all in flight before the first FMA (the accumulation order - key by key -
+  // is unchanged, so the result is the same bits as the one-key-per-iteration loop of decode_attn_task)
+  for (int j0 = warp; j0 < kvl; j0 += 16) {
+    float pj[4];
+    uint2 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 4 * u;
+      const int jc = j < kvl ? j : warp;  // clamped (the slot is in the tile): loaded, never used
+      pj[u] = s_scores[jc];
+      raw[u] = (jc == off) ? *reinterpret_cast<const uint2*>(sm.v + lane * 4)
+                           : *reinterpret_cast<const uint2*>(sV + v_half * tile_bytes + jc * 128 + ((v_unit ^ (jc & 7)) << 4) + v_sub);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 + 4 * u < kvl) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
+        const float2 a = __half22float2(h2[0]), bb = __half22float2(h2[1]);
+        acc[0] = fmaf(pj[u], a.x, acc[0]);
+        acc[1] = fmaf(pj[u], a.y, acc[1]);
+        acc[2] = fmaf(pj[u], bb.x, acc[2]);
+        acc[3] = fmaf(pj[u], bb.y, acc[3]);
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) sm.acc[warp][lane * 4 + i] = acc[i];
