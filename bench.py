@@ -365,7 +365,9 @@ def _ncu_traffic(kernel="gemv_kernel"):
     `ncu --set full` capture profiles/r2_ncu_raw.csv (written by scripts/gpu_round.sh from the same decode-step launch
     configuration). None when the capture is absent."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r2_ncu_raw.csv")
+    path = os.path.join(ROOT, "profiles", "r2_final_ncu_raw.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r2_ncu_raw.csv")
     if not os.path.exists(path):
         return None, None
     try:
@@ -458,7 +460,7 @@ def roofline_in_situ(eng, dims, dev, peaks, decode_events, new_tokens):
                       "inside the captured decode step" % B, "bound": "hbm",
             "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
             "frac_step": frac_step, "decode_step_ms": step_ms, "decode_steps_timed": tot_steps, "step_bytes": step_bytes,
-            "traffic": traffic, "traffic_source": ("profiles/r2_ncu_raw.csv: mean dram read+write of %d gemv_kernel launches under ncu --set full" % n_cap)
+            "traffic": traffic, "traffic_source": ("profiles/r2_final_ncu_raw.csv: mean dram read+write of %d gemv_kernel launches under ncu --set full" % n_cap)
             if traffic else None,
             "peak_source": peaks["src"], "avg_launch_us": avg_us, "launches_per_step": n_gemv,
             "avg_launch_us_after_dependency_wait": (kernel_us_after_wait / n_gemv) if kernel_us_after_wait else None,

@@ -85,5 +85,21 @@ for i in range(2):
     K.decode_attention(qd, B, 32, 128, pos, cos, cos, kc, vc, kvl, od, 1 / math.sqrt(128), cache_off=160, lora=(bq, bq, 8, 2.0))
     # the decode step's variant: K / V tiles by TMA into shared memory (visible cache bounded by 168 rows)
     K.decode_attention(qd, B, 32, 128, pos, cos, cos, kc, vc, kvl, od, 1 / math.sqrt(128), cache_off=160, lora=(bq, bq, 8, 2.0), kv_cap=168)
+# decode projections at the sweep's batch 16 (gemv_mt_kernel): qkv and gate/up + SwiGLU
+x16 = torch.randn(16, 4096, device=dev).half()
+for i in range(2):
+    K.gemm(x16, wq, w_static=True)
+    K.gemm(x16, wgu, act=K.ACT_SWIGLU, w_static=True)
+# decode attention over a long cache (decode_attn_stream_kernel): 4 sequences, 2064 visible tokens
+Sl = 2080
+kcl = torch.randn(B, Sl, Dl, device=dev).half()
+vcl = torch.randn(B, Sl, Dl, device=dev).half()
+posl = torch.full((B,), 2063, dtype=torch.int32, device=dev)
+kvll = torch.full((B,), 2064, dtype=torch.int32, device=dev)
+cosl = torch.randn(4096, 64, device=dev)
+wsl = torch.zeros(K.decode_attn_split_bytes(B, 32, Sl), device=dev, dtype=torch.uint8)
+for i in range(2):
+    K.decode_attention(qd, B, 32, 128, posl, cosl, cosl, kcl, vcl, kvll, od, 1 / math.sqrt(128), cache_off=2063, lora=(bq, bq, 8, 2.0),
+                       split_ws=wsl)
 torch.cuda.synchronize()
 print("done")
