@@ -3,13 +3,17 @@
 //
 //   O[b, i, h, :] = softmax_j( scale * Q[b, i, h, :] . K[b, j, h, :]  + mask ) V[b, j, h, :]
 //
-// One CTA (320 threads, 1 per SM) = TWO 128-query tiles of one (head, batch) running half a phase apart:
+// One CTA (576 threads, 1 per SM) = TWO 128-query tiles of one (head, batch) running half a phase apart:
 //   warp 0     TMA producer : Q tiles once; K_j and V_j tiles (BN = 128 keys) into 2-stage rings (128B-swizzled smem)
 //   warp 1     MMA issuer   : S_t = Q_t K_j^T (SS: both operands in smem) and O_t += P_t V_j (TS: A = P_t read from TENSOR
 //                             MEMORY, B = V_j MN-major from smem), accumulators S_0 S_1 O_0 O_1 in TMEM (4 x 128 columns)
-//   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1: one thread per query row (TMEM lane): tcgen05.ld S, online
-//              max / sum in fp32, exp2, P as packed fp16 written back OVER the S columns with tcgen05.st — P never touches
-//              shared memory. While one group does its softmax the tensor pipe runs the other tile's MMAs.
+//   warps 2-9  softmax of tile 0, warps 10-17 softmax of tile 1: TWO threads per query row (TMEM lane), 64 of the 128 score columns
+//              each (warp w may touch lanes 32 (w % 4) ..: the two halves of a row sit in warps w and w + 4): tcgen05.ld S, online
+//              max (the halves meet through shared memory + one 256-thread barrier per tile) / sum in fp32, exp2, P as packed
+//              fp16 written back OVER the S columns with tcgen05.st - P never touches shared memory. While one group does its
+//              softmax the tensor pipe runs the other tile's MMAs. (Round 2 first had 4 warps per tile, one thread per row: 2-3
+//              warps per scheduler at 168 registers left the issue slots 44 % busy with dependency stalls on top; 16 softmax
+//              warps double the warps per scheduler and halve the registers a thread holds.)
 // O stays in TMEM across KV tiles. The running maximum used for the exponentials is only moved when a row's maximum grew by
 // more than 2^8 since it was last fixed (then the row's O and sum are rescaled in TMEM); otherwise P is formed against the
 // older reference maximum (values <= 256, exact in the final normalisation because numerator and denominator share it).
@@ -28,7 +32,11 @@
 namespace myr {
 
 constexpr int A2_BN = 128;
-constexpr int A2_THREADS = 320;
+constexpr int A2_THREADS = 576;  // TMA warp + MMA warp + 2 x 8 softmax warps
+constexpr int A2_GROUP = 256;    // threads of one softmax group
+#ifndef A2_POLY_PER8
+#define A2_POLY_PER8 0            // of every 8 exponentials: how many take the FMA-pipe polynomial instead of the MUFU (0, 2 or 4; measured: 0 is fastest)
+#endif
 constexpr float A2_RESCALE_LOG2 = 8.0f;  // the reference maximum moves when a row's maximum grew by more than 2^8
 
 struct Attn2Params {
@@ -65,6 +73,21 @@ __device__ __forceinline__ float a2_exp2_poly(float x) {
   p = fmaf(p, f, 0.6931471806f);
   p = fmaf(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// the same for two arguments at once on Blackwell's packed fp32 pipe (FFMA2 / FADD2: one issue slot per pair): identical results
+__device__ __forceinline__ float2 a2_exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 t = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));
+  const float2 tm = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __ffma2_rn(tm, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.0096181291f, 0.0096181291f), make_float2(0.0555041087f, 0.0555041087f));
+  p = __ffma2_rn(p, f, make_float2(0.2402265070f, 0.2402265070f));
+  p = __ffma2_rn(p, f, make_float2(0.6931471806f, 0.6931471806f));
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
 }
 // D[tmem] (+)= A[tmem, fp16 packed two per column] * B[smem]
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -105,7 +128,7 @@ __device__ __forceinline__ void tma_store_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void a2_group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void a2_group_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(A2_GROUP) : "memory"); }
 
 // keys of KV tile j that the MMAs cover (multiple of 16) for a row of tiles that ends at key `kv_end`
 __device__ __forceinline__ int a2_tile_keys(int j, int kv_end) {
@@ -132,6 +155,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   uint64_t* bar_p = bars + 12;    // [2]  P_t written, O_t rescaled if needed (softmax group t -> MMA), 4 warp arrivals
   uint64_t* bar_o = bars + 14;    // [2]  all MMAs of tile t complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* s_xch = reinterpret_cast<float*>(bars + 18);  // [2 tiles][2 halves][128 rows] row maxima of the two column halves, then the same for the row sums
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -157,7 +181,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 4);
+      mbar_init(&bar_p[i], 8);
       mbar_init(&bar_o[i], 1);
     }
     fence_mbar_init();
@@ -257,61 +281,68 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
     }
   } else {
     // ------------------------------ softmax groups ------------------------------
-    const int t = (warp - 2) >> 2;       // query tile of this group
-    const int qw = warp & 3;             // TMEM lane quarter this warp may access
-    const int row = qw * 32 + lane;      // query row within the tile == TMEM lane
+    const int t = (warp - 2) >> 3;        // query tile of this group
+    const int half = ((warp - 2) >> 2) & 1;  // which 64 of the 128 score columns (and which half of the O columns) this thread owns
+    const int qw = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = qw * 32 + lane;       // query row within the tile == TMEM lane
     const int q_pos = p.q_off + q0 + 128 * t + row;
     const uint32_t t_s = tmem_base + (uint32_t(qw * 32) << 16) + t * 128;
     const uint32_t t_o = tmem_base + (uint32_t(qw * 32) << 16) + 256 + t * 128;
-    const int nch_o = p.dhp / 32;
-    float m_run = -INFINITY, m_ref = 0.f, l_run = 0.f;
+    const int nch_o = p.dhp / 32;         // 32-column chunks of O; this thread owns chunks [oc0, oc1)
+    const int oc0 = half ? (nch_o + 1) / 2 : 0, oc1 = half ? nch_o : (nch_o + 1) / 2;
+    float* xch_mine = s_xch + (t * 2 + half) * 128 + row;
+    const float* xch_other = s_xch + (t * 2 + (half ^ 1)) * 128 + row;
+    float m_run = -INFINITY, m_ref = 0.f, l_run = 0.f;  // l_run: this half's share of the row sum
     for (int j = 0; j < nt[t]; ++j) {
       const int k0 = j * A2_BN;
       const int n = a2_tile_keys(j, kv_end[t]);
-      const int n32 = (n + 31) >> 5;  // 32-column TMEM loads that cover the tile
+      const int n32 = (n + 31) >> 5;  // 32-column TMEM loads that cover the tile; this thread's are 2 half, 2 half + 1
       mbar_wait(&bar_s[t], (uint32_t)(j & 1));
       tc_fence_after();
-      // the whole score row lives in registers: one TMEM read per tile, all loads in flight before the single wait
-      uint32_t sr[4][32];
+      // this thread's half of the score row lives in registers: all loads in flight before the single wait
+      uint32_t sr[2][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < n32) tmem_ld32(t_s + c * 32, sr[c]);
+      for (int c = 0; c < 2; ++c)
+        if (2 * half + c < n32) tmem_ld32(t_s + (2 * half + c) * 32, sr[c]);
       tmem_ld_wait();
       const bool edge = (k0 + n32 * 32 > kv_len) || (p.causal && (k0 + n32 * 32 - 1 > p.q_off + q0 + 128 * t));
       if (edge) {  // masked keys become -inf: they drop out of the maximum and exp2 turns them into exact zeros
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < n32) {
+        for (int c = 0; c < 2; ++c) {
+          if (2 * half + c < n32) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int key = k0 + c * 32 + i;
+              const int key = k0 + (2 * half + c) * 32 + i;
               if (!(key < kv_len && (!p.causal || key <= q_pos))) sr[c][i] = 0xff800000u;
             }
           }
         }
       }
-      // ---- row maximum: four independent chains
+      // ---- row maximum: four independent chains over this half, then the other half's through shared memory
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < n32) {
+      for (int c = 0; c < 2; ++c) {
+        if (2 * half + c < n32) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sr[c][i]));
         }
       }
-      const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      *xch_mine = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      a2_group_sync(2 + t);  // also: both halves have their scores in registers, so P may overwrite the S columns below
+      const float m_tile = fmaxf(*xch_mine, *xch_other);
       const float m_new = fmaxf(m_run, m_tile);
       if (j == 0) {
         m_ref = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked row so far: everything stays zero
       } else {
-        // O_t += P_t V_{j-1} is complete (S_t of this tile was issued after it): O_t may be rescaled in place
+        // O_t += P_t V_{j-1} is complete (S_t of this tile was issued after it): O_t may be rescaled in place. Both halves of a
+        // row take the same decision (same m_run / m_ref / m_new) and each rescales its own O columns.
         const bool need = (m_new - m_ref) * p.scale_log2 > A2_RESCALE_LOG2 || (m_run == -INFINITY && m_new != -INFINITY);
         if (__any_sync(0xffffffffu, need)) {
           // nothing accumulated yet (every earlier key masked): O and l are exactly zero, alpha = 0 keeps them so (and finite)
           const float alpha = need ? (m_run == -INFINITY ? 0.f : a2_exp2((m_ref - m_new) * p.scale_log2)) : 1.0f;
           if (need) m_ref = m_new;
           l_run *= alpha;
-          for (int c = 0; c < 2 * nch_o; ++c) {  // 16 columns at a time: the score row stays in registers meanwhile
+          for (int c = 2 * oc0; c < 2 * oc1; ++c) {  // 16 columns at a time: the score row stays in registers meanwhile
             uint32_t r[16];
             tmem_ld16(t_o + c * 16, r);
             tmem_ld_wait();
@@ -323,36 +354,65 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       m_run = m_new;
       const float moff = m_ref * p.scale_log2;
-      // ---- P = exp2(s * scale_log2 - moff) -> packed fp16 over the first columns of S_t; row sum in fp32 (four chains)
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      // ---- P = exp2(s * scale_log2 - moff) -> packed fp16 over the first columns of S_t; row sum in fp32. Four elements per step:
+      // the scale / offset and the row-sum additions are packed fp32 pairs (FFMA2 / FADD2), elements 0 and 2 take the MUFU, 1 and 3
+      // the polynomial as one packed evaluation: ~5 issue slots per probability instead of ~9 (the softmax groups are issue-bound)
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), mo2 = make_float2(-moff, -moff);
+      float2 acc_m = make_float2(0.f, 0.f), acc_p = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < n32) {
+      for (int c = 0; c < 2; ++c) {
+        if (2 * half + c < n32) {
           uint32_t(&packed)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sr[c][0]);  // pairs are packed over the scores already consumed
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = a2_exp2(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, -moff));
-            const float p1 = a2_exp2_poly(fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, -moff));
-            ls[(i >> 1) & 3] += p0 + p1;
-            const __half2 hp = __floats2half2_rn(p0, p1);
-            packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+          for (int i = 0; i < 32; i += 8) {
+            float2 z[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              z[q] = __ffma2_rn(make_float2(__uint_as_float(sr[c][i + 2 * q]), __uint_as_float(sr[c][i + 2 * q + 1])), sc2, mo2);
+            float pr[8];
+            if (A2_POLY_PER8 == 4) {  // elements 1, 3, 5, 7 by the packed polynomial, 0, 2, 4, 6 on the MUFU
+              const float2 pa = a2_exp2_poly2(make_float2(z[0].y, z[1].y)), pb = a2_exp2_poly2(make_float2(z[2].y, z[3].y));
+              pr[1] = pa.x; pr[3] = pa.y; pr[5] = pb.x; pr[7] = pb.y;
+            } else if (A2_POLY_PER8 == 2) {  // elements 1 and 5
+              const float2 pa = a2_exp2_poly2(make_float2(z[0].y, z[2].y));
+              pr[1] = pa.x; pr[5] = pa.y;
+              pr[3] = a2_exp2(z[1].y); pr[7] = a2_exp2(z[3].y);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) pr[2 * q + 1] = a2_exp2(z[q].y);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pr[2 * q] = a2_exp2(z[q].x);
+            acc_m = __fadd2_rn(acc_m, make_float2(pr[0], pr[1]));
+            acc_p = __fadd2_rn(acc_p, make_float2(pr[2], pr[3]));
+            acc_m = __fadd2_rn(acc_m, make_float2(pr[4], pr[5]));
+            acc_p = __fadd2_rn(acc_p, make_float2(pr[6], pr[7]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __half2 hq = __floats2half2_rn(pr[2 * q], pr[2 * q + 1]);
+              packed[(i >> 1) + q] = *reinterpret_cast<const uint32_t*>(&hq);
+            }
           }
-          tmem_st16(t_s + c * 16, packed);
+          tmem_st16(t_s + (2 * half + c) * 16, packed);
         }
       }
+      const float ls[4] = {acc_m.x, acc_m.y, acc_p.x, acc_p.y};
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[t]);
-    }
+        }
     // ---- finalise: O / l -> fp16 -> swizzled rows in the dead Q tile -> TMA store
     if (nt[t] > 0) {
+      xch_mine[512] = l_run;  // own slots: the partner may still be reading the last tile's maxima
       mbar_wait(&bar_o[t], 0);
       tc_fence_after();
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      a2_group_sync(2 + t);
+      const float l_row = half ? (xch_other[512] + xch_mine[512]) : (xch_mine[512] + xch_other[512]);  // low half + high half, in both threads
+      const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
       uint8_t* stage = sQ + t * tile_bytes;
-      for (int c = 0; c < nch_o; ++c) {
+      for (int c = oc0; c < oc1; ++c) {
         uint32_t r[32];
         tmem_ld32(t_o + c * 32, r);
         tmem_ld_wait();
@@ -371,7 +431,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       fence_proxy_async_smem();
       a2_group_sync(2 + t);
-      if (row == 0) {
+      if (row == 0 && half == 0) {
         for (int db = 0; db < p.DB; ++db) tma_store_4d(&tmO, stage + db * 16384, db * 64, h, q0 + 128 * t, b);
         tma_store_commit_wait();
       }
@@ -417,7 +477,7 @@ int attn2_launch(const myr_attn_args* a, cudaStream_t stream) {
       if (rc) return rc;
     }
   }
-  const size_t smem_bytes = (size_t)6 * p.DB * 16384 + 1024 + 256;
+  const size_t smem_bytes = (size_t)6 * p.DB * 16384 + 1024 + 256 + 2 * 2 * 2 * 128 * 4;
   dim3 grid(ceil_div(a->Sq, 256), a->H, a->B);
   static bool attr_set = false;
   if (!attr_set) {
