@@ -380,6 +380,14 @@ def test_decode_attention_long_cache_split(K, O, off):
     _decode_attention_case(K, O, True, 0, B=2, H=4, Smax=2080, past=[off, off - 5], off=off, split=True)
 
 
+@pytest.mark.parametrize("B,H,Smax,off", [(16, 32, 320, 290), (1, 32, 320, 299), (32, 32, 320, 258), (5, 32, 1100, 1050), (3, 8, 4100, 4090)])
+def test_decode_attention_stream_many_rows(K, O, B, H, Smax, off):
+    """The persistent long-cache kernel at the throughput sweep's shapes: batch 16 / 32 with 32 heads (several (row, head) segments per
+    CTA, segments cut between CTAs and combined from partial results), a single row (fewer chunks than SMs: every (row, head) is split
+    over three CTAs), five rows over 1050 slots, a 4090-slot cache. Same references as the other decode-attention tests."""
+    _decode_attention_case(K, O, True, 0, B=B, H=H, Smax=Smax, past=[off - (i % 7) for i in range(B)], off=off, split=True)
+
+
 def _decode_attention_case(K, O, lora, kv_cap, B, H, Smax, past, off, split=False):
     """myr_decode_attention (one launch per decode step and layer) against the prefill pair myr_rope_cache + myr_attention_fwd
     on the same cache, and against the oracle's rotary / attention arithmetic."""
