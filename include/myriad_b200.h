@@ -333,6 +333,19 @@ int myr_col2im(const void* dcols, void* din, int32_t B, int32_t H, int32_t W, in
                void* stream);
 
 
+/* ---- LoRA branches of q_proj / v_proj in training (peft, myriad.py:171-178: y += s * B (A dropout(x)), rank 8), CUDA-core kernels: as
+ * tcgen05 GEMMs with F = 8 or K = 8 these cost 15-20 us per launch. Dropout masks are regenerated from (seed, offset + t * D + d) as in
+ * myr_dropout_fwd (p = 0: none); off_q / off_v are the mask streams of the two branches. All summation orders are fixed.
+ * fwd: xa fp32 [T, 16] = [drop_q(x1) A_q^T | drop_v(x1) A_v^T] (A fp16 [16, D] = A_q rows then A_v rows), then
+ *      qkv[t, col_q + d] += s * xa[t, 0:8] . B_q[d, :],  qkv[t, col_v + d] += s * xa[t, 8:16] . B_v[d, :]   (qkv fp16, B fp16 [D, 8]).
+ * bwd: d_xa (scratch fp32 [T, 16]) = s * dY B;  dB_j fp32 [D, 8] = s * inv_scale * dY_j^T xa_j;  dA fp32 [16, D] = inv_scale * d_xa^T drop(x1);
+ *      dx1 fp32 [T, D] += mask_j * d_xa_j A_j (branch q first, then v). dY_j = dqkv[:, col_j : col_j + D] (fp16). */
+int myr_lora_fwd(const void* x1, int64_t ldx, const void* A, const void* bq, const void* bv, void* xa, void* qkv, int64_t ldq, int64_t col_q,
+                 int64_t col_v, int32_t T, int32_t D, int32_t r, float s, float p, uint64_t seed, uint64_t off_q, uint64_t off_v, void* stream);
+int myr_lora_bwd(const void* dqkv, int64_t ldq, int64_t col_q, int64_t col_v, const void* xa, const void* A, const void* bq, const void* bv,
+                 const void* x1, int64_t ldx, void* dxa_scratch, void* dbq, void* dbv, void* dA, void* dx1, int64_t ldd, int32_t T, int32_t D,
+                 int32_t r, float s, float inv_scale, float p, uint64_t seed, uint64_t off_q, uint64_t off_v, void* stream);
+
 /* ---- vision expert heads (adrefexpert_v2.py:245-301); the ImageBind-Huge trunk (imagebind_model.py:486-504,
  * transformer.py:104-170) runs on myr_patchify / myr_gemm_f16 / myr_norm / myr_attention_fwd ----------------------------------- */
 /* tokens[i].transpose(0,1)[:, 1:, :] (adrefexpert_v2.py:26-27,215-216): x fp32 [B, N, D] -> out fp16 [B, N-1, D] without the class

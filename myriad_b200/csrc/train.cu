@@ -337,6 +337,37 @@ __global__ void rope_bwd_kernel(__half* __restrict__ dqkv, long long ld, int T, 
   }
 }
 
+// 16-byte variant: one thread = 8 rotary pairs (dh / 2 a multiple of 8, row stride a multiple of 8, 16-byte aligned base)
+__global__ void rope_bwd_vec8_kernel(__half* __restrict__ dqkv, long long ld, int T, int H, int dh, const int* __restrict__ pos,
+                                     const float* __restrict__ cos_t, const float* __restrict__ sin_t) {
+  const int half = dh >> 1, hv = half >> 3;
+  const long long total = (long long)T * 2 * H * hv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % hv) << 3;
+    long long r = i / hv;
+    const int h = (int)(r % H);
+    r /= H;
+    const int which = (int)(r % 2);
+    const long long t = r / 2;
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + (size_t)pos[t] * half + j);
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + (size_t)pos[t] * half + j);
+    const float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w}, sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    __half* p = dqkv + t * ld + (size_t)which * H * dh + h * dh;
+    uint4 r1 = *reinterpret_cast<const uint4*>(p + j), r2 = *reinterpret_cast<const uint4*>(p + half + j);
+    __half2* a2 = reinterpret_cast<__half2*>(&r1);
+    __half2* b2 = reinterpret_cast<__half2*>(&r2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 d1 = __half22float2(a2[k]), d2 = __half22float2(b2[k]);
+      a2[k] = __floats2half2_rn(d1.x * c[2 * k] + d2.x * sn[2 * k], d1.y * c[2 * k + 1] + d2.y * sn[2 * k + 1]);
+      b2[k] = __floats2half2_rn(d2.x * c[2 * k] - d1.x * sn[2 * k], d2.y * c[2 * k + 1] - d1.y * sn[2 * k + 1]);
+    }
+    *reinterpret_cast<uint4*>(p + j) = r1;
+    *reinterpret_cast<uint4*>(p + half + j) = r2;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // attention backward helpers on materialised score rows [n_rows = B*H*Sq, ld] (Sq, Skv <= a few hundred)
 //   softmax: P = softmax(scale * S + mask) fp16; key j visible iff j < kv_len[b] && (!causal || j <= i); pad cols -> 0
@@ -769,9 +800,15 @@ extern "C" int myr_rope_bwd(void* dqkv, int64_t ld, int32_t T, int32_t H, int32_
                             const void* sin_table, void* stream_) {
   STREAM;
   MYR_CHECK_ARG(dqkv && pos && cos_table && sin_table && T > 0 && dh % 2 == 0, "rope_bwd: bad arguments");
-  rope_bwd_kernel<<<grid_for((long long)T * 2 * H * (dh / 2), 256), 256, 0, stream>>>(
-      reinterpret_cast<__half*>(dqkv), ld, T, H, dh, reinterpret_cast<const int*>(pos), reinterpret_cast<const float*>(cos_table),
-      reinterpret_cast<const float*>(sin_table));
+  if ((dh / 2) % 8 == 0 && ld % 8 == 0 && ((reinterpret_cast<uintptr_t>(dqkv) | reinterpret_cast<uintptr_t>(cos_table) |
+                                           reinterpret_cast<uintptr_t>(sin_table)) & 15) == 0)
+    rope_bwd_vec8_kernel<<<grid_for((long long)T * 2 * H * (dh / 16), 256), 256, 0, stream>>>(
+        reinterpret_cast<__half*>(dqkv), ld, T, H, dh, reinterpret_cast<const int*>(pos), reinterpret_cast<const float*>(cos_table),
+        reinterpret_cast<const float*>(sin_table));
+  else
+    rope_bwd_kernel<<<grid_for((long long)T * 2 * H * (dh / 2), 256), 256, 0, stream>>>(
+        reinterpret_cast<__half*>(dqkv), ld, T, H, dh, reinterpret_cast<const int*>(pos), reinterpret_cast<const float*>(cos_table),
+        reinterpret_cast<const float*>(sin_table));
   MYR_CHECK_LAUNCH();
   return MYR_OK;
 }
@@ -884,5 +921,312 @@ extern "C" int myr_memset_zero(void* ptr, size_t bytes, void* stream_) {
   STREAM;
   MYR_CHECK_ARG(ptr != nullptr, "memset_zero: null pointer");
   MYR_CHECK_CUDA(cudaMemsetAsync(ptr, 0, bytes, stream));
+  return MYR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// LoRA branches of q_proj / v_proj (peft, myriad.py:171-178; y += s * B (A dropout(x))) as CUDA-core kernels. The rank is 8: as
+// tcgen05 GEMMs (F = 8 or K = 8 against 128 x BN tiles) the ten launches per layer of the backward and the six of the forward
+// cost 15-20 us each - 8 ms of a 44 ms training step for 0.03 % of its flops. Here: fp16 operands, fp32 accumulation, the dropout
+// mask regenerated from (seed, offset + t * D + d) wherever the dropped input is needed (nothing stored), fixed summation orders.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace myr {
+
+constexpr int LR = 8;  // rank
+
+__device__ __forceinline__ void lr_unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+// dropped input as the GEMM path saw it: rn_f16(x * keep_scale) where kept, 0 elsewhere (p = 0: thresh = 0 keeps everything)
+__device__ __forceinline__ float lr_drop(float x, uint32_t thresh, float keep_scale, unsigned long long seed, unsigned long long idx) {
+  if (thresh == 0) return x;
+  return drop_hash(seed, idx) >= thresh ? __half2float(__float2half_rn(x * keep_scale)) : 0.f;
+}
+
+// xa[t, j * 8 + k] = sum_d drop_j(x1[t, d]) * A[j * 8 + k, d]: one warp = TWO tokens, both branches, lane = 8 consecutive d per step;
+// the four warps of a block walk A together (one pass over its 16 rows per 8 tokens: 10 MB of L2 traffic per launch instead of 84)
+__global__ void __launch_bounds__(128) lora_xa_fwd_kernel(const __half* __restrict__ x1, long long ldx, const __half* __restrict__ A,
+                                                         float* __restrict__ xa, int T, int D, uint32_t thresh, float keep_scale,
+                                                         unsigned long long seed, unsigned long long off_q, unsigned long long off_v) {
+  const int t0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 2, lane = threadIdx.x & 31;
+  if (t0 >= T) return;
+  const bool two = t0 + 1 < T;
+  float acc[2][2 * LR];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int k = 0; k < 2 * LR; ++k) acc[u][k] = 0.f;
+  for (int d0 = lane * 8; d0 < D; d0 += 256) {
+    float xq[2][8], xv[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float x[8];
+      lr_unpack8(*reinterpret_cast<const uint4*>(x1 + (size_t)(two || u == 0 ? t0 + u : t0) * ldx + d0), x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const unsigned long long idx = (unsigned long long)(t0 + u) * D + d0 + e;
+        xq[u][e] = lr_drop(x[e], thresh, keep_scale, seed, off_q + idx);
+        xv[u][e] = lr_drop(x[e], thresh, keep_scale, seed, off_v + idx);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * LR; ++k) {
+      float a[8];
+      lr_unpack8(__ldg(reinterpret_cast<const uint4*>(A + (size_t)k * D + d0)), a);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float* xs = k < LR ? xq[u] : xv[u];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[u][k] = fmaf(xs[e], a[e], acc[u][k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int k = 0; k < 2 * LR; ++k) {
+      const float v = warp_sum_t(acc[u][k]);
+      if (lane == 0 && (u == 0 || two)) xa[(size_t)(t0 + u) * 2 * LR + k] = v;
+    }
+}
+
+// qkv[t, col_j + d] = rn_f16(qkv[t, col_j + d] + s * sum_k xa[t, j * 8 + k] * B_j[d, k]): one thread = 8 consecutive d of one branch
+// for EIGHT tokens (its 8 rows of B stay in registers)
+__global__ void lora_b_apply_kernel(__half* __restrict__ qkv, long long ldq, const float* __restrict__ xa, const __half* __restrict__ bq,
+                                    const __half* __restrict__ bv, int T, int D, float s, long long col_q, long long col_v) {
+  const int dv = D >> 3;
+  const int tg = (T + 7) >> 3;
+  const long long total = (long long)tg * 2 * dv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d0 = (int)(i % dv) << 3;
+    const long long r = i / dv;
+    const int j = (int)(r & 1);
+    const int tb = (int)(r >> 1) << 3;
+    const __half* B = j ? bv : bq;
+    float b[8][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) lr_unpack8(__ldg(reinterpret_cast<const uint4*>(B + (size_t)(d0 + e) * LR)), b[e]);
+#pragma unroll 2
+    for (int t = tb; t < min(T, tb + 8); ++t) {
+      const float4 xa0 = *reinterpret_cast<const float4*>(xa + (size_t)t * 2 * LR + j * LR), xa1 = *reinterpret_cast<const float4*>(xa + (size_t)t * 2 * LR + j * LR + 4);
+      const float xk[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xa1.x, xa1.y, xa1.z, xa1.w};
+      __half* dst = qkv + (size_t)t * ldq + (j ? col_v : col_q) + d0;
+      float y[8];
+      lr_unpack8(*reinterpret_cast<const uint4*>(dst), y);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a = fmaf(xk[k], b[e][k], a);
+        y[e] = fmaf(s, a, y[e]);
+      }
+      uint4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(y[2 * e], y[2 * e + 1]);
+      *reinterpret_cast<uint4*>(dst) = o;
+    }
+  }
+}
+
+// d_xa[t, j * 8 + k] = s * sum_d dy_j[t, d] * B_j[d, k]: one warp = FOUR tokens of one branch (B is read once per four tokens)
+__global__ void __launch_bounds__(256) lora_dxa_kernel(const __half* __restrict__ dqkv, long long ldq, const __half* __restrict__ bq,
+                                                      const __half* __restrict__ bv, float* __restrict__ dxa, int T, int D, float s,
+                                                      long long col_q, long long col_v) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int tq = (T + 3) >> 2;
+  if (w >= 2 * tq) return;
+  const int j = w & 1, t0 = (w >> 1) << 2;
+  const __half* B = j ? bv : bq;
+  float acc[4][LR];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int k = 0; k < LR; ++k) acc[u][k] = 0.f;
+  for (int d0 = lane * 8; d0 < D; d0 += 256) {
+    float g[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      lr_unpack8(*reinterpret_cast<const uint4*>(dqkv + (size_t)min(t0 + u, T - 1) * ldq + (j ? col_v : col_q) + d0), g[u]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float b[8];
+      lr_unpack8(__ldg(reinterpret_cast<const uint4*>(B + (size_t)(d0 + e) * LR)), b);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < LR; ++k) acc[u][k] = fmaf(g[u][e], b[k], acc[u][k]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int k = 0; k < LR; ++k) {
+      const float v = warp_sum_t(acc[u][k]);
+      if (lane == 0 && t0 + u < T) dxa[(size_t)(t0 + u) * 2 * LR + j * LR + k] = s * v;
+    }
+}
+
+// Column reductions over the tokens. A block = 64 columns (two per thread) x 8 token slices; the slices meet in shared memory in slice order.
+//   dB_j[d, k] = alpha_b * sum_t dy_j[t, d] * xa[t, j * 8 + k]                     (which = 0, 1: branch q, v)
+//   dA[j * 8 + k, d] = alpha_a * sum_t d_xa[t, j * 8 + k] * drop_j(x1[t, d])      (which = 2, 3)
+__global__ void __launch_bounds__(256) lora_wgrad_kernel(const __half* __restrict__ dqkv, long long ldq, const float* __restrict__ xa,
+                                                        const float* __restrict__ dxa, const __half* __restrict__ x1, long long ldx,
+                                                        float* __restrict__ dbq, float* __restrict__ dbv, float* __restrict__ dA, int T, int D,
+                                                        float alpha_b, float alpha_a, long long col_q, long long col_v, uint32_t thresh,
+                                                        float keep_scale, unsigned long long seed, unsigned long long off_q,
+                                                        unsigned long long off_v) {
+  __shared__ float red[8][64][LR + 1];
+  const int which = blockIdx.y, j = which & 1;
+  const int dl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int d = blockIdx.x * 64 + 2 * dl;  // D is a multiple of 256: every block is full
+  float acc[2][LR];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int k = 0; k < LR; ++k) acc[u][k] = 0.f;
+  {
+    const int per = (T + 7) / 8;
+    const int t0 = sl * per, t1 = min(T, t0 + per);
+    const float* coef = (which < 2 ? xa : dxa) + j * LR;
+    const unsigned long long off = j ? off_v : off_q;
+    const __half* src = which < 2 ? dqkv + (j ? col_v : col_q) + d : x1 + d;
+    const long long ld = which < 2 ? ldq : ldx;
+#pragma unroll 4
+    for (int t = t0; t < t1; ++t) {
+      const float2 raw = __half22float2(*reinterpret_cast<const __half2*>(src + (size_t)t * ld));
+      float v0 = raw.x, v1 = raw.y;
+      if (which >= 2) {
+        const unsigned long long idx = off + (unsigned long long)t * D + d;
+        v0 = lr_drop(v0, thresh, keep_scale, seed, idx);
+        v1 = lr_drop(v1, thresh, keep_scale, seed, idx + 1);
+      }
+      const float4 c0 = *reinterpret_cast<const float4*>(coef + (size_t)t * 2 * LR), c1 = *reinterpret_cast<const float4*>(coef + (size_t)t * 2 * LR + 4);
+      const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int k = 0; k < LR; ++k) {
+        acc[0][k] = fmaf(v0, c[k], acc[0][k]);
+        acc[1][k] = fmaf(v1, c[k], acc[1][k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int k = 0; k < LR; ++k) red[sl][2 * dl + u][k] = acc[u][k];
+  __syncthreads();
+  // 512 (column, rank index) sums per block, two per thread: the 8 slices added in slice order
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int o = threadIdx.x + rep * 256;
+    const int c = o >> 3, k = o & 7;
+    float tot = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 8; ++s2) tot += red[s2][c][k];
+    const int dd = blockIdx.x * 64 + c;
+    if (which < 2)
+      (j ? dbv : dbq)[(size_t)dd * LR + k] = alpha_b * tot;
+    else
+      dA[(size_t)(j * LR + k) * D + dd] = alpha_a * tot;
+  }
+}
+
+// d_x1[t, d] += sum_j keep_j(t, d) * keep_scale * sum_k d_xa[t, j * 8 + k] * A[j * 8 + k, d]: one thread = 4 consecutive d
+__global__ void lora_dx_kernel(float* __restrict__ dx1, long long ldd, const float* __restrict__ dxa, const __half* __restrict__ A, int T, int D,
+                               uint32_t thresh, float keep_scale, unsigned long long seed, unsigned long long off_q,
+                               unsigned long long off_v) {
+  const int dv = D >> 2;
+  const long long total = (long long)T * dv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d0 = (int)(i % dv) << 2;
+    const long long t = i / dv;
+    float c[2 * LR];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(dxa + t * 2 * LR + 4 * q);
+      c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+    }
+    float g[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int k = 0; k < 2 * LR; ++k) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(A + (size_t)k * D + d0);
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+      float* gj = g[k / LR];
+      gj[0] = fmaf(c[k], lo.x, gj[0]); gj[1] = fmaf(c[k], lo.y, gj[1]); gj[2] = fmaf(c[k], hi.x, gj[2]); gj[3] = fmaf(c[k], hi.y, gj[3]);
+    }
+    float4 acc = *reinterpret_cast<const float4*>(dx1 + t * ldd + d0);
+    float* ap = reinterpret_cast<float*>(&acc);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned long long idx = (unsigned long long)t * D + d0 + e;
+      // branch q first, then v: the order the two dropout_bwd_add launches of the GEMM path added them in
+      if (thresh == 0) {
+        ap[e] += g[0][e];
+        ap[e] += g[1][e];
+      } else {
+        if (drop_hash(seed, off_q + idx) >= thresh) ap[e] += g[0][e] * keep_scale;
+        if (drop_hash(seed, off_v + idx) >= thresh) ap[e] += g[1][e] * keep_scale;
+      }
+    }
+    *reinterpret_cast<float4*>(dx1 + t * ldd + d0) = acc;
+  }
+}
+
+}  // namespace myr
+
+using namespace myr;
+
+extern "C" int myr_lora_fwd(const void* x1, int64_t ldx, const void* A, const void* bq, const void* bv, void* xa, void* qkv, int64_t ldq,
+                            int64_t col_q, int64_t col_v, int32_t T, int32_t D, int32_t r, float s, float p, uint64_t seed, uint64_t off_q,
+                            uint64_t off_v, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(x1 && A && bq && bv && xa && qkv && T > 0 && D > 0 && D % 256 == 0 && r == LR && p >= 0.f && p < 1.f, "lora_fwd: bad arguments (rank 8, D %% 256 == 0)");
+  MYR_CHECK_ARG(ldx % 8 == 0 && ldq % 8 == 0 && col_q % 8 == 0 && col_v % 8 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(bq) | reinterpret_cast<uintptr_t>(bv) |
+                      reinterpret_cast<uintptr_t>(xa) | reinterpret_cast<uintptr_t>(qkv)) & 15) == 0,
+                "lora_fwd: operands must be 16-byte aligned");
+  const uint32_t th = p > 0.f ? drop_thresh(p) : 0u;
+  lora_xa_fwd_kernel<<<ceil_div(T, 8), 128, 0, stream>>>(reinterpret_cast<const __half*>(x1), ldx, reinterpret_cast<const __half*>(A),
+                                                         reinterpret_cast<float*>(xa), T, D, th, 1.0f / (1.0f - p), seed, off_q, off_v);
+  MYR_CHECK_LAUNCH();
+  lora_b_apply_kernel<<<grid_for((long long)ceil_div(T, 8) * 2 * (D / 8), 128), 128, 0, stream>>>(reinterpret_cast<__half*>(qkv), ldq, reinterpret_cast<const float*>(xa),
+                                                                                    reinterpret_cast<const __half*>(bq), reinterpret_cast<const __half*>(bv), T, D,
+                                                                                    s, col_q, col_v);
+  MYR_CHECK_LAUNCH();
+  return MYR_OK;
+}
+
+extern "C" int myr_lora_bwd(const void* dqkv, int64_t ldq, int64_t col_q, int64_t col_v, const void* xa, const void* A, const void* bq,
+                            const void* bv, const void* x1, int64_t ldx, void* dxa_scratch, void* dbq, void* dbv, void* dA, void* dx1,
+                            int64_t ldd, int32_t T, int32_t D, int32_t r, float s, float inv_scale, float p, uint64_t seed, uint64_t off_q,
+                            uint64_t off_v, void* stream_) {
+  STREAM;
+  MYR_CHECK_ARG(dqkv && xa && A && bq && bv && x1 && dxa_scratch && dbq && dbv && dA && dx1 && T > 0 && D > 0 && D % 256 == 0 && r == LR &&
+                    p >= 0.f && p < 1.f,
+                "lora_bwd: bad arguments (rank 8, D %% 256 == 0)");
+  MYR_CHECK_ARG(ldq % 8 == 0 && ldx % 8 == 0 && ldd % 4 == 0 && col_q % 8 == 0 && col_v % 8 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(dqkv) | reinterpret_cast<uintptr_t>(xa) | reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(bq) |
+                      reinterpret_cast<uintptr_t>(bv) | reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(dxa_scratch) |
+                      reinterpret_cast<uintptr_t>(dx1)) & 15) == 0,
+                "lora_bwd: operands must be 16-byte aligned");
+  const uint32_t th = p > 0.f ? drop_thresh(p) : 0u;
+  const float ks = 1.0f / (1.0f - p);
+  lora_dxa_kernel<<<ceil_div(2 * ceil_div(T, 4), 8), 256, 0, stream>>>(reinterpret_cast<const __half*>(dqkv), ldq, reinterpret_cast<const __half*>(bq),
+                                                          reinterpret_cast<const __half*>(bv), reinterpret_cast<float*>(dxa_scratch), T, D, s, col_q, col_v);
+  MYR_CHECK_LAUNCH();
+  lora_wgrad_kernel<<<dim3(D / 64, 4), 256, 0, stream>>>(reinterpret_cast<const __half*>(dqkv), ldq, reinterpret_cast<const float*>(xa),
+                                                                  reinterpret_cast<const float*>(dxa_scratch), reinterpret_cast<const __half*>(x1), ldx,
+                                                                  reinterpret_cast<float*>(dbq), reinterpret_cast<float*>(dbv), reinterpret_cast<float*>(dA), T, D,
+                                                                  s * inv_scale, inv_scale, col_q, col_v, th, ks, seed, off_q, off_v);
+  MYR_CHECK_LAUNCH();
+  lora_dx_kernel<<<grid_for((long long)T * (D / 4), 256), 256, 0, stream>>>(reinterpret_cast<float*>(dx1), ldd, reinterpret_cast<const float*>(dxa_scratch),
+                                                                           reinterpret_cast<const __half*>(A), T, D, th, ks, seed, off_q, off_v);
+  MYR_CHECK_LAUNCH();
   return MYR_OK;
 }

@@ -577,3 +577,21 @@ def expert_rowmax(S, ld, acc, rows, R, weight, accumulate):
 
 def expert_sim_maps(sim, maps, simmask, B, G, OUT):
     check(lib().myr_expert_sim_maps(_p(sim), _p(maps), _p(simmask), B, G, OUT, _stream()), "myr_expert_sim_maps")
+
+
+# ---- LoRA branches in training (csrc/train.cu; peft semantics of myriad.py:171-178, rank 8)
+def lora_fwd(x1, A, bq, bv, xa, qkv, col_q, col_v, s, p=0.0, seed=0, off_q=0, off_v=0):
+    T, D = x1.shape
+    assert x1.dtype == A.dtype == bq.dtype == bv.dtype == qkv.dtype == torch.float16 and xa.dtype == torch.float32
+    assert A.shape == (16, D) and A.is_contiguous() and bq.is_contiguous() and bv.is_contiguous() and xa.is_contiguous()
+    check(lib().myr_lora_fwd(_p(x1), _i64(x1.stride(0)), _p(A), _p(bq), _p(bv), _p(xa), _p(qkv), _i64(qkv.stride(0)), _i64(col_q), _i64(col_v),
+                             T, D, 8, _f32(s), _f32(p), _u64(seed), _u64(off_q), _u64(off_v), _stream()), "myr_lora_fwd")
+
+
+def lora_bwd(dqkv, col_q, col_v, xa, A, bq, bv, x1, dxa, dbq, dbv, dA, dx1, s, inv_scale, p=0.0, seed=0, off_q=0, off_v=0):
+    T, D = x1.shape
+    assert dqkv.dtype == torch.float16 and xa.dtype == dxa.dtype == dbq.dtype == dbv.dtype == dA.dtype == dx1.dtype == torch.float32
+    assert dbq.is_contiguous() and dbv.is_contiguous() and dA.is_contiguous() and dxa.is_contiguous()
+    check(lib().myr_lora_bwd(_p(dqkv), _i64(dqkv.stride(0)), _i64(col_q), _i64(col_v), _p(xa), _p(A), _p(bq), _p(bv), _p(x1), _i64(x1.stride(0)),
+                             _p(dxa), _p(dbq), _p(dbv), _p(dA), _p(dx1), _i64(dx1.stride(0)), T, D, 8, _f32(s), _f32(inv_scale), _f32(p), _u64(seed),
+                             _u64(off_q), _u64(off_v), _stream()), "myr_lora_bwd")

@@ -43,6 +43,8 @@ class MyriadTrainer(MyriadEngine):
         self.lora_dropout, self.dropout_seed, self.fwd_count = float(lora_dropout), int(dropout_seed), 0
         self.overlap_allreduce = True
         self._early = None
+        # MYR_LORA_FUSED=0: the LoRA branches as tcgen05 GEMMs + separate dropout launches (16 launches per layer instead of 5)
+        self.lora_fused = os.environ.get("MYR_LORA_FUSED", "1") != "0" and dims.lora_r == 8 and dims.llama.hidden % 256 == 0
         self.supervised_rows_only = True  # lm_head / clamp-CE only on the rows that carry a target (False: all positions, as the reference)
         self._sd_for_flat = sd
         super().__init__(sd, dims, device, max_batch, max_seq)
@@ -544,7 +546,13 @@ class MyriadTrainer(MyriadEngine):
             K.norm(h, L.n1, None, l.eps, rms=True, out16=Sv.x1)
             Sv.qkv = K.gemm(Sv.x1, L.wqkv)
             Sv.xa = Sv.xd = None
-            if L.lora is not None:
+            if L.lora is not None and self.lora_fused:
+                # both LoRA branches in two CUDA-core launches (rank 8 is no GEMM shape): xa = drop(x1) A^T, qkv += s * xa B^T; the
+                # dropout masks are regenerated wherever the dropped input is needed, so no dropped copy of x1 is kept
+                Sv.xa = self._e(T, 2 * self.d.lora_r, dtype=F32)
+                K.lora_fwd(Sv.x1, L.lora.a, L.lora.bq, L.lora.bv, Sv.xa, Sv.qkv, 0, 2 * D, L.lora.scale, self.lora_dropout, self.dropout_seed,
+                           self._lora_drop_offset(li, 0, T * D), self._lora_drop_offset(li, 1, T * D))
+            elif L.lora is not None:
                 r = self.d.lora_r
                 if self.lora_dropout > 0.0:
                     # peft: each LoRA module drops its own copy of the input: B_q(A_q(drop_q(x))) and B_v(A_v(drop_v(x)))
@@ -614,7 +622,15 @@ class MyriadTrainer(MyriadEngine):
                            B, H, S, S, dh, att_scale, True, tp.kv_len)
             K.rope_bwd(dqkv, T, H, dh, tp.pos, self.llw.cos, self.llw.sin)
             d_x1 = self._dgrad(dqkv, L, "wqkv", out_dtype=F32)
-            if L.lora is not None:
+            if L.lora is not None and self.lora_fused:
+                r = self.d.lora_r
+                p = "llama_model.base_model.model.model.layers.%d.self_attn." % li
+                o = self.segments[p + "q_proj.lora_A.default.weight"][0]
+                K.lora_bwd(dqkv, 0, 2 * D, Sv.xa, L.lora.a, L.lora.bq, L.lora.bv, Sv.x1, self._e(T, 2 * r, dtype=F32),
+                           self.grad(p + "q_proj.lora_B.default.weight"), self.grad(p + "v_proj.lora_B.default.weight"),
+                           self.flat_grads[o:o + 2 * r * D].view(2 * r, D), d_x1, L.lora.scale, inv_scale, self.lora_dropout, self.dropout_seed,
+                           self._lora_drop_offset(li, 0, T * D), self._lora_drop_offset(li, 1, T * D))
+            elif L.lora is not None:
                 r = self.d.lora_r
                 p = "llama_model.base_model.model.model.layers.%d.self_attn." % li
                 s = L.lora.scale
