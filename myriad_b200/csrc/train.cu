@@ -2,6 +2,7 @@
 // clamp-CE loss fwd+bwd, LayerNorm/RMSNorm backward, SwiGLU / GELU backward, RoPE backward, masked row softmax and
 // its backward (attention backward = batched tcgen05 GEMMs around these), row gather/scatter, LoraAdaptorV2 wgrad,
 // column sums (bias / base_prompts grads), fused AdamW over the flat parameter buffer.
+#include <type_traits>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -506,29 +507,34 @@ __global__ void colsum_kernel(const void* __restrict__ src, int src_dtype, long 
 }
 
 // Same sums with the rows spread over a block (the default; MYR_COLSUM_BLOCK=0 selects the one-thread-per-column kernel
-// above). One block per 32 columns, 32 warps: warp w adds the rows
-// w, w + 32, ... (coalesced 32-column reads), the 32 partial sums per column meet in shared memory and are added in warp order:
-// deterministic, and a bias gradient over 12 544 rows is ~400 dependent adds per thread instead of 12 544.
+// above). One block per `cpb` columns (32, or fewer where 32 would leave most SMs without a block: a 64-channel conv bias over
+// 12 544 rows ran 235 us on two blocks), 1024 threads: thread (ry, cx) adds the rows ry, ry + 1024 / cpb, ... of column cx, the
+// 1024 / cpb partial sums per column meet in shared memory and are added in ry order: deterministic.
 __global__ void __launch_bounds__(1024) colsum_block_kernel(const void* __restrict__ src, int src_dtype, long long ld, long long gs, int groups,
-                                                      int rows, int D, float scale, float* __restrict__ out, int accumulate) {
-  __shared__ float part[32][33];
-  const int cx = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
+                                                      int rows, int D, float scale, float* __restrict__ out, int accumulate, int cpb) {
+  __shared__ float part[1024];
+  const int cx = threadIdx.x % cpb, ry = threadIdx.x / cpb, nry = 1024 / cpb;
+  const int c = blockIdx.x * cpb + cx;
   float a = 0.f;
   if (c < D) {
     const long long total = (long long)groups * rows;
-    for (long long i = wy; i < total; i += 32) {
-      const long long g = i / rows, r = i - g * rows;
-      const long long o = g * gs + r * ld + c;
-      a += src_dtype == MYR_F32 ? reinterpret_cast<const float*>(src)[o] : __half2float(reinterpret_cast<const __half*>(src)[o]);
+    if (groups == 1 && src_dtype == MYR_F16) {  // the bias gradients: no 64-bit division per element
+      const __half* s16 = reinterpret_cast<const __half*>(src) + c;
+#pragma unroll 8
+      for (int r = ry; r < rows; r += nry) a += __half2float(s16[(long long)r * ld]);
+    } else {
+      for (long long i = ry; i < total; i += nry) {
+        const long long g = i / rows, r = i - g * rows;
+        const long long o = g * gs + r * ld + c;
+        a += src_dtype == MYR_F32 ? reinterpret_cast<const float*>(src)[o] : __half2float(reinterpret_cast<const __half*>(src)[o]);
+      }
     }
   }
-  part[wy][cx] = a;
+  part[threadIdx.x] = a;
   __syncthreads();
-  if (wy == 0 && c < D) {
+  if (ry == 0 && c < D) {
     float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 32; ++w) t += part[w][cx];
+    for (int w = 0; w < nry; ++w) t += part[w * cpb + cx];
     out[c] = (accumulate ? out[c] : 0.f) + scale * t;
   }
 }
@@ -560,21 +566,47 @@ __global__ void adaptor_bwd_rows_kernel(const float* __restrict__ x, const float
       td[(size_t)warp * 2 * rank + rank + r] = dt[r];
     }
 }
-__global__ void adaptor_bwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ td,
-                                        float* __restrict__ dw1, float* __restrict__ dw2, int rows, int D, int rank, float scale) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= D) return;
+// a block = 32 columns x 16 row slices; the slices meet in shared memory and are added in slice order (one thread per column walking
+// all 1028 rows took 585 us for 11.6 MB)
+__global__ void __launch_bounds__(512) adaptor_bwd_cols_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              const float* __restrict__ td, float* __restrict__ dw1,
+                                                              float* __restrict__ dw2, int rows, int D, int rank, float scale) {
+  __shared__ float red[16][32][9];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cl;
   float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int row = 0; row < rows; ++row) {
-    const float xv = x[(size_t)row * D + i], dv = dy[(size_t)row * D + i];
-    for (int r = 0; r < rank; ++r) {
-      a2[r] += dv * td[(size_t)row * 2 * rank + r];
-      a1[r] += td[(size_t)row * 2 * rank + rank + r] * xv;
+  if (i < D) {
+    const int per = (rows + 15) / 16;
+    const int r0 = sl * per, r1 = min(rows, r0 + per);
+#pragma unroll 4
+    for (int row = r0; row < r1; ++row) {
+      const float xv = __ldg(x + (size_t)row * D + i), dv = __ldg(dy + (size_t)row * D + i);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (r < rank) {
+          a2[r] = fmaf(dv, __ldg(td + (size_t)row * 2 * rank + r), a2[r]);
+          a1[r] = fmaf(__ldg(td + (size_t)row * 2 * rank + rank + r), xv, a1[r]);
+        }
     }
   }
-  for (int r = 0; r < rank; ++r) {
-    dw2[(size_t)i * rank + r] = scale * a2[r];
-    dw1[(size_t)r * D + i] = scale * a1[r];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    red[sl][cl][r] = a1[r];
+    red[sl][cl][4 + r] = a2[r];
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    const int c = threadIdx.x >> 3, q = threadIdx.x & 7, r = q & 3;
+    const int col = blockIdx.x * 32 + c;
+    if (col < D && r < rank) {
+      float tot = 0.f;
+#pragma unroll
+      for (int s2 = 0; s2 < 16; ++s2) tot += red[s2][c][q];
+      if (q < 4)
+        dw1[(size_t)r * D + col] = scale * tot;
+      else
+        dw2[(size_t)col * rank + r] = scale * tot;
+    }
   }
 }
 
@@ -639,15 +671,19 @@ __global__ void check_finite_kernel(const float* __restrict__ g, long long n, in
 
 // ---------------------------------------------------------------------------------------------------
 // LoRA dropout (peft: lora_dropout = 0.05 on the INPUT of each LoRA branch, myriad.py:171-178). Counter-based mask:
-// element idx of a step's stream keeps its value iff hash(seed, idx) >= p * 2^32 (splitmix64 finaliser), kept values are
-// scaled by 1 / (1 - p). The backward recomputes the same mask from (seed, offset), nothing is stored.
+// element idx of a step's stream keeps its value iff hash(seed, idx) >= p * 2^32, kept values are scaled by 1 / (1 - p). The
+// backward recomputes the same mask from (seed, offset), nothing is stored. The hash is a 32-bit multiply-xorshift mixer (two
+// rounds) over the index folded with the seed: ~10 integer instructions per element. (The first version was the 64-bit splitmix
+// finaliser, ~30 instructions: at 2 x 2.7 M elements per LoRA kernel the mask generation alone was ~18 us of each launch.)
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t drop_hash(unsigned long long seed, unsigned long long idx) {
-  unsigned long long z = seed + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (uint32_t)(z >> 32);
+  uint32_t h = (uint32_t)idx * 0x9E3779B1u + ((uint32_t)(idx >> 32) + (uint32_t)seed) * 0x85EBCA77u + (uint32_t)(seed >> 32);
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
 }
 __global__ void dropout_fwd_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ out, long long ldo, int rows, int D,
                                    uint32_t thresh, float keep_scale, unsigned long long seed, unsigned long long offset) {
@@ -865,8 +901,12 @@ extern "C" int myr_colsum(const void* src, int32_t src_dtype, int64_t ld, int64_
     block_variant = (e && e[0] == '0') ? 0 : 1;
   }
   if (block_variant)
-    colsum_block_kernel<<<ceil_div(D, 32), 1024, 0, stream>>>(src, src_dtype, ld, group_stride, groups, rows, D, scale,
-                                                             reinterpret_cast<float*>(out), accumulate);
+  {
+    int cpb = 32;
+    while (cpb > 4 && ceil_div(D, cpb) < 64) cpb >>= 1;
+    colsum_block_kernel<<<ceil_div(D, cpb), 1024, 0, stream>>>(src, src_dtype, ld, group_stride, groups, rows, D, scale,
+                                                              reinterpret_cast<float*>(out), accumulate, cpb);
+  }
   else
     colsum_kernel<<<ceil_div(D, 128), 128, 0, stream>>>(src, src_dtype, ld, group_stride, groups, rows, D, scale,
                                                        reinterpret_cast<float*>(out), accumulate);
@@ -882,7 +922,7 @@ extern "C" int myr_adaptor_bwd(const void* x, const void* dy, const void* w1, co
       reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(w1),
       reinterpret_cast<const float*>(w2), reinterpret_cast<float*>(scratch), rows, D, rank);
   MYR_CHECK_LAUNCH();
-  adaptor_bwd_cols_kernel<<<ceil_div(D, 128), 128, 0, stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(dy),
+  adaptor_bwd_cols_kernel<<<ceil_div(D, 32), 512, 0, stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(dy),
                                                                reinterpret_cast<const float*>(scratch), reinterpret_cast<float*>(dw1),
                                                                reinterpret_cast<float*>(dw2), rows, D, rank, scale);
   MYR_CHECK_LAUNCH();
@@ -945,8 +985,11 @@ __device__ __forceinline__ void lr_unpack8(const uint4& u, float (&f)[8]) {
 }
 // dropped input as the GEMM path saw it: rn_f16(x * keep_scale) where kept, 0 elsewhere (p = 0: thresh = 0 keeps everything)
 __device__ __forceinline__ float lr_drop(float x, uint32_t thresh, float keep_scale, unsigned long long seed, unsigned long long idx) {
-  if (thresh == 0) return x;
-  return drop_hash(seed, idx) >= thresh ? __half2float(__float2half_rn(x * keep_scale)) : 0.f;
+  // branch-free, also for p = 0 (thresh = 0 keeps everything and keep_scale = 1 leaves the fp16 value as it is): a test per
+  // element, even a uniform one, cuts the unrolled loops into 32 short dependent chains
+  const float v = __half2float(__float2half_rn(x * keep_scale));
+  const int keep = -(int)(drop_hash(seed, idx) >= thresh);
+  return __int_as_float(__float_as_int(v) & keep);
 }
 
 // xa[t, j * 8 + k] = sum_d drop_j(x1[t, d]) * A[j * 8 + k, d]: one warp = TWO tokens, both branches, lane = 8 consecutive d per step;
@@ -967,7 +1010,7 @@ __global__ void __launch_bounds__(128) lora_xa_fwd_kernel(const __half* __restri
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       float x[8];
-      lr_unpack8(*reinterpret_cast<const uint4*>(x1 + (size_t)(two || u == 0 ? t0 + u : t0) * ldx + d0), x);
+      lr_unpack8(__ldg(reinterpret_cast<const uint4*>(x1 + (size_t)min(t0 + u, T - 1) * ldx + d0)), x);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const unsigned long long idx = (unsigned long long)(t0 + u) * D + d0 + e;
@@ -1036,10 +1079,10 @@ __global__ void lora_b_apply_kernel(__half* __restrict__ qkv, long long ldq, con
 }
 
 // d_xa[t, j * 8 + k] = s * sum_d dy_j[t, d] * B_j[d, k]: one warp = FOUR tokens of one branch (B is read once per four tokens)
-__global__ void __launch_bounds__(256) lora_dxa_kernel(const __half* __restrict__ dqkv, long long ldq, const __half* __restrict__ bq,
+__global__ void __launch_bounds__(128) lora_dxa_kernel(const __half* __restrict__ dqkv, long long ldq, const __half* __restrict__ bq,
                                                       const __half* __restrict__ bv, float* __restrict__ dxa, int T, int D, float s,
                                                       long long col_q, long long col_v) {
-  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int tq = (T + 3) >> 2;
   if (w >= 2 * tq) return;
   const int j = w & 1, t0 = (w >> 1) << 2;
@@ -1073,16 +1116,16 @@ __global__ void __launch_bounds__(256) lora_dxa_kernel(const __half* __restrict_
     }
 }
 
-// Column reductions over the tokens. A block = 64 columns (two per thread) x 8 token slices; the slices meet in shared memory in slice order.
+// Column reductions over the tokens. A block = 64 columns (two per thread) x 16 token slices; the slices meet in shared memory in slice order.
 //   dB_j[d, k] = alpha_b * sum_t dy_j[t, d] * xa[t, j * 8 + k]                     (which = 0, 1: branch q, v)
 //   dA[j * 8 + k, d] = alpha_a * sum_t d_xa[t, j * 8 + k] * drop_j(x1[t, d])      (which = 2, 3)
-__global__ void __launch_bounds__(256) lora_wgrad_kernel(const __half* __restrict__ dqkv, long long ldq, const float* __restrict__ xa,
+__global__ void __launch_bounds__(512) lora_wgrad_kernel(const __half* __restrict__ dqkv, long long ldq, const float* __restrict__ xa,
                                                         const float* __restrict__ dxa, const __half* __restrict__ x1, long long ldx,
                                                         float* __restrict__ dbq, float* __restrict__ dbv, float* __restrict__ dA, int T, int D,
                                                         float alpha_b, float alpha_a, long long col_q, long long col_v, uint32_t thresh,
                                                         float keep_scale, unsigned long long seed, unsigned long long off_q,
                                                         unsigned long long off_v) {
-  __shared__ float red[8][64][LR + 1];
+  __shared__ float red[16][64][LR + 1];
   const int which = blockIdx.y, j = which & 1;
   const int dl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int d = blockIdx.x * 64 + 2 * dl;  // D is a multiple of 256: every block is full
@@ -1092,28 +1135,35 @@ __global__ void __launch_bounds__(256) lora_wgrad_kernel(const __half* __restric
 #pragma unroll
     for (int k = 0; k < LR; ++k) acc[u][k] = 0.f;
   {
-    const int per = (T + 7) / 8;
+    const int per = (T + 15) / 16;
     const int t0 = sl * per, t1 = min(T, t0 + per);
     const float* coef = (which < 2 ? xa : dxa) + j * LR;
     const unsigned long long off = j ? off_v : off_q;
     const __half* src = which < 2 ? dqkv + (j ? col_v : col_q) + d : x1 + d;
     const long long ld = which < 2 ? ldq : ldx;
-#pragma unroll 4
-    for (int t = t0; t < t1; ++t) {
-      const float2 raw = __half22float2(*reinterpret_cast<const __half2*>(src + (size_t)t * ld));
+    auto body = [&](int t, auto drop) {
+      const float2 raw = __half22float2(__ldg(reinterpret_cast<const __half2*>(src + (size_t)t * ld)));
       float v0 = raw.x, v1 = raw.y;
-      if (which >= 2) {
+      if (decltype(drop)::value) {
         const unsigned long long idx = off + (unsigned long long)t * D + d;
         v0 = lr_drop(v0, thresh, keep_scale, seed, idx);
         v1 = lr_drop(v1, thresh, keep_scale, seed, idx + 1);
       }
-      const float4 c0 = *reinterpret_cast<const float4*>(coef + (size_t)t * 2 * LR), c1 = *reinterpret_cast<const float4*>(coef + (size_t)t * 2 * LR + 4);
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(coef + (size_t)t * 2 * LR)), c1 = __ldg(reinterpret_cast<const float4*>(coef + (size_t)t * 2 * LR + 4));
       const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
       for (int k = 0; k < LR; ++k) {
         acc[0][k] = fmaf(v0, c[k], acc[0][k]);
         acc[1][k] = fmaf(v1, c[k], acc[1][k]);
       }
+    };
+    // two loops, not one with the test inside: a branch in the body keeps the unrolled iterations' loads from being issued together
+    if (which < 2) {
+#pragma unroll 4
+      for (int t = t0; t < t1; ++t) body(t, std::false_type{});
+    } else {
+#pragma unroll 4
+      for (int t = t0; t < t1; ++t) body(t, std::true_type{});
     }
   }
 #pragma unroll
@@ -1121,14 +1171,13 @@ __global__ void __launch_bounds__(256) lora_wgrad_kernel(const __half* __restric
 #pragma unroll
     for (int k = 0; k < LR; ++k) red[sl][2 * dl + u][k] = acc[u][k];
   __syncthreads();
-  // 512 (column, rank index) sums per block, two per thread: the 8 slices added in slice order
-#pragma unroll
-  for (int rep = 0; rep < 2; ++rep) {
-    const int o = threadIdx.x + rep * 256;
+  // 512 (column, rank index) sums per block, one per thread: the 16 slices added in slice order
+  {
+    const int o = threadIdx.x;
     const int c = o >> 3, k = o & 7;
     float tot = 0.f;
 #pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2) tot += red[s2][c][k];
+    for (int s2 = 0; s2 < 16; ++s2) tot += red[s2][c][k];
     const int dd = blockIdx.x * 64 + c;
     if (which < 2)
       (j ? dbv : dbq)[(size_t)dd * LR + k] = alpha_b * tot;
@@ -1166,13 +1215,11 @@ __global__ void lora_dx_kernel(float* __restrict__ dx1, long long ldd, const flo
     for (int e = 0; e < 4; ++e) {
       const unsigned long long idx = (unsigned long long)t * D + d0 + e;
       // branch q first, then v: the order the two dropout_bwd_add launches of the GEMM path added them in
-      if (thresh == 0) {
-        ap[e] += g[0][e];
-        ap[e] += g[1][e];
-      } else {
-        if (drop_hash(seed, off_q + idx) >= thresh) ap[e] += g[0][e] * keep_scale;
-        if (drop_hash(seed, off_v + idx) >= thresh) ap[e] += g[1][e] * keep_scale;
-      }
+      // (selects, not branches; p = 0: thresh = 0 keeps everything and keep_scale = 1)
+      const float nq = fmaf(g[0][e], keep_scale, ap[e]);
+      ap[e] = drop_hash(seed, off_q + idx) >= thresh ? nq : ap[e];
+      const float nv = fmaf(g[1][e], keep_scale, ap[e]);
+      ap[e] = drop_hash(seed, off_v + idx) >= thresh ? nv : ap[e];
     }
     *reinterpret_cast<float4*>(dx1 + t * ldd + d0) = acc;
   }
@@ -1217,10 +1264,10 @@ extern "C" int myr_lora_bwd(const void* dqkv, int64_t ldq, int64_t col_q, int64_
                 "lora_bwd: operands must be 16-byte aligned");
   const uint32_t th = p > 0.f ? drop_thresh(p) : 0u;
   const float ks = 1.0f / (1.0f - p);
-  lora_dxa_kernel<<<ceil_div(2 * ceil_div(T, 4), 8), 256, 0, stream>>>(reinterpret_cast<const __half*>(dqkv), ldq, reinterpret_cast<const __half*>(bq),
+  lora_dxa_kernel<<<ceil_div(2 * ceil_div(T, 4), 4), 128, 0, stream>>>(reinterpret_cast<const __half*>(dqkv), ldq, reinterpret_cast<const __half*>(bq),
                                                           reinterpret_cast<const __half*>(bv), reinterpret_cast<float*>(dxa_scratch), T, D, s, col_q, col_v);
   MYR_CHECK_LAUNCH();
-  lora_wgrad_kernel<<<dim3(D / 64, 4), 256, 0, stream>>>(reinterpret_cast<const __half*>(dqkv), ldq, reinterpret_cast<const float*>(xa),
+  lora_wgrad_kernel<<<dim3(D / 64, 4), 512, 0, stream>>>(reinterpret_cast<const __half*>(dqkv), ldq, reinterpret_cast<const float*>(xa),
                                                                   reinterpret_cast<const float*>(dxa_scratch), reinterpret_cast<const __half*>(x1), ldx,
                                                                   reinterpret_cast<float*>(dbq), reinterpret_cast<float*>(dbv), reinterpret_cast<float*>(dA), T, D,
                                                                   s * inv_scale, inv_scale, col_q, col_v, th, ks, seed, off_q, off_v);
