@@ -23,7 +23,13 @@ SHAPES = [  # name, T, F, K, kwargs
     ("llama o+res", 524, 4096, 4096, dict(res="f32")),
     ("llama gate/up swiglu", 524, 22016, 4096, dict(act=K.ACT_SWIGLU)),
     ("llama down+res", 524, 4096, 11008, dict(res="f32")),
+    ("train qkv", 656, 12304, 4096, dict()),
+    ("train o+res", 656, 4096, 4096, dict(res="f32")),
     ("train gate/up", 656, 22016, 4096, dict()),
+    ("train down+res", 656, 4096, 11008, dict(res="f32")),
+    ("train d_down", 656, 11008, 4096, dict()),
+    ("train d_gate/up", 656, 4096, 22016, dict()),
+    ("train d_qkv", 656, 4096, 12288, dict()),
     ("s2048 gate/up swiglu", 8192, 22016, 4096, dict(act=K.ACT_SWIGLU)),
     ("s2048 down+res", 8192, 4096, 11008, dict(res="f32")),
 ]
