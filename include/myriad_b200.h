@@ -305,6 +305,16 @@ int myr_softmax_rows(const void* S, int64_t lds, void* P, int64_t ldp, int32_t B
                      float scale, int32_t causal, const void* kv_len, void* stream);
 int myr_softmax_bwd_rows(const void* P, int64_t ldp, const void* dP, int64_t lddp, void* dS, int64_t lds, int64_t n_rows,
                          int32_t cols, float scale, void* stream);
+/* Fused attention backward for short sequences (dh 64 / 128, Skv <= 256): dQ, dK, dV from Q, K, V, dO in one launch, the
+ * scores never leave the SM. Replaces the autograd backward of the eager softmax(Q K^T * scale + mask) V of
+ * modeling_llama.py:196-222 / Qformer.py:180-260. Operands fp16 with head stride dh, token stride *_ts and row (batch) stride *_bs
+ * in elements (multiples of 8); mask as myr_softmax_rows (causal needs Sq == Skv; kv_len int32 [B] or NULL). */
+int myr_attn_bwd_small_supported(int32_t Sq, int32_t Skv, int32_t dh);
+int myr_attn_bwd_small(const void* q, int64_t q_ts, int64_t q_bs, const void* k, int64_t k_ts, int64_t k_bs, const void* v,
+                       int64_t v_ts, int64_t v_bs, const void* dO, int64_t do_ts, int64_t do_bs, void* dq, int64_t dq_ts,
+                       int64_t dq_bs, void* dk, int64_t dk_ts, int64_t dk_bs, void* dv, int64_t dv_ts, int64_t dv_bs, int32_t B,
+                       int32_t H, int32_t Sq, int32_t Skv, int32_t dh, float scale, int32_t causal, const void* kv_len,
+                       void* stream);
 /* dst[r] = src[idx[r]] (scatter = 0) or dst[idx[r]] = src[r] (scatter = 1), with dtype cast; idx int32 device. */
 int myr_index_rows(const void* src, int32_t src_dtype, int64_t src_ld, void* dst, int32_t dst_dtype, int64_t dst_ld,
                    const void* idx, int32_t R, int32_t D, int32_t scatter, void* stream);

@@ -511,6 +511,18 @@ def softmax_bwd_rows(P, dP, dS, n_rows, cols, scale):
                                      _stream()), "myr_softmax_bwd_rows")
 
 
+def attn_bwd_small_supported(Sq, Skv, dh):
+    return bool(lib().myr_attn_bwd_small_supported(Sq, Skv, dh))
+
+
+def attn_bwd_small(q, k, v, dctx, dq, dk, dv, B, H, Sq, Skv, dh, scale, causal=False, kv_len=None):
+    """q / k / v / dq / dk / dv: (tensor view at head 0, token stride, row stride); dctx fp16 [B * Sq, H * dh]."""
+    a = []
+    for t, ts, bs in (q, k, v, (dctx, H * dh, Sq * H * dh), dq, dk, dv):
+        a += [_p(t), _i64(ts), _i64(bs)]
+    check(lib().myr_attn_bwd_small(*a, B, H, Sq, Skv, dh, _f32(scale), int(causal), _p(kv_len), _stream()), "myr_attn_bwd_small")
+
+
 def index_rows(src, dst, idx, D, scatter=False):
     assert idx.dtype == torch.int32
     check(lib().myr_index_rows(_p(src), _dt(src), _i64(src.stride(0)), _p(dst), _dt(dst), _i64(dst.stride(0)), _p(idx), idx.numel(), D,

@@ -287,14 +287,21 @@ class MyriadTrainer(MyriadEngine):
 
     # --------------------------------------------------------------------------------------- attention backward
     ATTN_BWD_WS_BYTES = int(os.environ.get("MYR_ATTN_BWD_WS_MB", "1024")) << 20
+    ATTN_BWD_FUSED = os.environ.get("MYR_ATTN_BWD_FUSED", "1") != "0"
 
     def _attn_bwd(self, q, k, v, dctx, dq, dk, dv, B, H, Sq, Skv, dh, scale, causal, kv_len):
         """q/k/v/dq/dk/dv: (tensor_view, token_stride, batch_stride) with head stride dh; dctx fp16 [B*Sq, H*dh].
+        Short sequences (dh 64 / 128, Skv <= 256: every attention of the training step but the Q-Former's 257-key cross-attention)
+        take the fused kernel of csrc/attn_bwd.cu. Otherwise
         P is re-materialised: S = Q K^T (batched tcgen05 GEMM, fp32) -> masked softmax -> dV = P^T dO, dP = dO V^T,
         dS = scale * P * (dP - rowsum(dP * P)), dQ = dS K, dK = dS^T Q.
         Heads are independent, so the S x S work buffers (8 bytes per score) are sized for a GROUP of heads that fits
         ATTN_BWD_WS_BYTES and the group loop walks the heads: 164-token training sequences take one pass (27 MB), the sweep's
         S = 2048 at batch 4 takes 5 passes of 7 heads (0.94 GB each) instead of one 4.3 GB allocation per layer."""
+        if self.ATTN_BWD_FUSED and K.attn_bwd_small_supported(Sq, Skv, dh):
+            # short sequences (the training step's): one fused launch, scores stay on the SM (csrc/attn_bwd.cu)
+            K.attn_bwd_small(q, k, v, dctx, dq, dk, dv, B, H, Sq, Skv, dh, scale, causal, kv_len)
+            return
         dev = self.dev
         Sp = (Skv + 63) // 64 * 64
         per_head = B * Sq * Sp * 8

@@ -136,9 +136,14 @@ def test_swiglu_gelu_rope_bwd(K, O):
 
 @pytest.mark.parametrize("cfg", [dict(B=2, H=2, Sq=40, Skv=40, dh=128, causal=True, kv=(40, 33)),
                                  dict(B=2, H=12, Sq=81, Skv=257, dh=64, causal=False, kv=None),
-                                 dict(B=1, H=3, Sq=81, Skv=81, dh=64, causal=False, kv=None)])
+                                 dict(B=1, H=3, Sq=81, Skv=81, dh=64, causal=False, kv=None),
+                                 dict(B=2, H=4, Sq=164, Skv=164, dh=128, causal=True, kv=(164, 150)),
+                                 dict(B=1, H=2, Sq=256, Skv=256, dh=128, causal=True, kv=None),
+                                 dict(B=2, H=2, Sq=33, Skv=250, dh=64, causal=False, kv=(250, 7)),
+                                 dict(B=1, H=1, Sq=5, Skv=3, dh=128, causal=False, kv=None)])
 def test_attention_bwd(cfg):
-    """Trainer._attn_bwd (batched tcgen05 GEMMs around the masked row softmax) against autograd."""
+    """Trainer._attn_bwd against autograd: the fused short-sequence kernel (csrc/attn_bwd.cu) where it applies, and the batched
+    tcgen05 GEMMs around the masked row softmax (the long-sequence path) on every shape."""
     from myriad_b200.training import MyriadTrainer
     torch.manual_seed(3)
     B, H, Sq, Skv, dh = cfg["B"], cfg["H"], cfg["Sq"], cfg["Skv"], cfg["dh"]
@@ -162,18 +167,31 @@ def test_attention_bwd(cfg):
     tr.dev = torch.device("cuda:0")
     c = lambda t: t.detach().reshape(-1, HD).half().cuda().contiguous()
     qd, kd, vd, dod = c(q), c(k), c(v), c(do)
-    dq, dk, dv = torch.zeros_like(qd), torch.zeros_like(kd), torch.zeros_like(vd)
     kv_len = torch.tensor(cfg["kv"], dtype=torch.int32, device="cuda") if cfg["kv"] is not None else None
-    tr._attn_bwd((qd, HD, Sq * HD), (kd, HD, Skv * HD), (vd, HD, Skv * HD), dod, (dq, HD, Sq * HD), (dk, HD, Skv * HD),
-                 (dv, HD, Skv * HD), B, H, Sq, Skv, dh, scale, cfg["causal"], kv_len)
-    eq, ek, ev = rel(dq, q.grad.reshape(-1, HD)), rel(dk, k.grad.reshape(-1, HD)), rel(dv, v.grad.reshape(-1, HD))
-    print("attention bwd %s: dq %.2e dk %.2e dv %.2e" % (cfg, eq, ek, ev))
-    assert max(eq, ek, ev) < TOL_UNIT
+
+    def run():
+        dq, dk, dv = torch.full_like(qd, float("nan")), torch.full_like(kd, float("nan")), torch.full_like(vd, float("nan"))
+        tr._attn_bwd((qd, HD, Sq * HD), (kd, HD, Skv * HD), (vd, HD, Skv * HD), dod, (dq, HD, Sq * HD), (dk, HD, Skv * HD),
+                     (dv, HD, Skv * HD), B, H, Sq, Skv, dh, scale, cfg["causal"], kv_len)
+        eq, ek, ev = rel(dq, q.grad.reshape(-1, HD)), rel(dk, k.grad.reshape(-1, HD)), rel(dv, v.grad.reshape(-1, HD))
+        assert max(eq, ek, ev) < TOL_UNIT, (eq, ek, ev)
+        return dq, dk, dv, (eq, ek, ev)
+
+    from myriad_b200 import kernels as K_mod
+    fused_ok = K_mod.attn_bwd_small_supported(Sq, Skv, dh)
+    assert fused_ok == (Skv <= 256)
+    if fused_ok:
+        tr.ATTN_BWD_FUSED = True
+        a = run()
+        print("attention bwd fused %s: dq %.2e dk %.2e dv %.2e" % ((cfg,) + a[3]))
+        b = run()
+        assert all(torch.equal(x, y) for x, y in zip(a[:3], b[:3]))  # fixed-order reductions: run to run identical
+    tr.ATTN_BWD_FUSED = False
+    dq, dk, dv, e = run()
+    print("attention bwd GEMM path %s: dq %.2e dk %.2e dv %.2e" % ((cfg,) + e))
     # bounded work buffers: one head per pass (the S = 2048 sweep shape takes 5 passes) must give the same bits
     tr.ATTN_BWD_WS_BYTES = B * Sq * ((Skv + 63) // 64 * 64) * 8
-    dq2, dk2, dv2 = torch.zeros_like(qd), torch.zeros_like(kd), torch.zeros_like(vd)
-    tr._attn_bwd((qd, HD, Sq * HD), (kd, HD, Skv * HD), (vd, HD, Skv * HD), dod, (dq2, HD, Sq * HD), (dk2, HD, Skv * HD),
-                 (dv2, HD, Skv * HD), B, H, Sq, Skv, dh, scale, cfg["causal"], kv_len)
+    dq2, dk2, dv2, _ = run()
     assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
 
 
