@@ -24,5 +24,12 @@ rc_graph=$?
 MYR_SANITIZE=1 timeout ${T_SAN:-900} $SAN --tool memcheck --print-limit 20 --error-exitcode 86 \
     python -m pytest tests/test_expert_gpu.py -m gpu -q -x -k "not full_width" > gpurun_out/sanitize_expert.log 2>&1
 echo "memcheck vision expert: exit $? | $(grep -E 'ERROR SUMMARY' gpurun_out/sanitize_expert.log | tail -1) | $(grep -E 'passed|failed' gpurun_out/sanitize_expert.log | tail -1)" >> gpurun_out/sanitize_summary.txt
+# the training-side kernels (fused attention backward, fused LoRA kernels, conv / adaptor reductions) under memcheck and racecheck
+for tool in memcheck racecheck; do
+  MYR_SANITIZE=1 timeout ${T_SAN:-900} $SAN --tool $tool --print-limit 20 --error-exitcode 86 \
+      python -m pytest tests/test_training_gpu.py -m gpu -q -x -k "attention_bwd or lora_dropout or conv_trunk or norm_bwd or swiglu_gelu_rope or clamp_ce" \
+      > gpurun_out/sanitize_train_${tool}.log 2>&1
+  echo "$tool training kernels: exit $? | $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_train_${tool}.log | tail -1) | $(grep -E 'passed|failed' gpurun_out/sanitize_train_${tool}.log | tail -1)" >> gpurun_out/sanitize_summary.txt
+done
 echo "memcheck decode graph: exit $rc_graph | $(grep -E 'ERROR SUMMARY' gpurun_out/sanitize_decode_graph.log | tail -1) | $(grep -E 'passed|failed' gpurun_out/sanitize_decode_graph.log | tail -1)" >> gpurun_out/sanitize_summary.txt
 cat gpurun_out/sanitize_summary.txt
