@@ -22,6 +22,10 @@ SHAPES = {
     "tr_gu": (656, 22016, 4096, dict()),
     "qf_kv": (1028, 9216, 1408, dict(bias=True)),
     "small": (300, 768, 768, dict(bias=True)),
+    "tr_o": (656, 4096, 4096, dict(res=True)),
+    "tr_down": (656, 4096, 11008, dict(res=True)),
+    "tr_dqkv": (656, 4096, 12288, dict(res=True)),
+    "tr_dgu": (656, 4096, 22016, dict(res=True)),
 }
 
 GROUPS = {
@@ -49,6 +53,8 @@ GROUPS = {
             ("vit_fc1", 0, 208, 1, 1), ("qf_kv", 0, 208, 1, 1)],
     "mc": [(sh, 0, bn, P, 1) for sh, bn in (("big_gu", 256), ("big_down", 256), ("ll_gu", 176), ("ll_qkv", 176), ("vit_fc1", 176), ("tr_gu", 224), ("qf_kv", 208))
            for P in (1, 2, 4)],
+    "tr": [(sh, 0, bn, 1, S) for sh in ("tr_o", "tr_down", "tr_dqkv", "tr_dgu") for bn, S in ((176, 1), (224, 1), (224, 2), (224, 3), (176, 2), (256, 3))] +
+          [(sh, 0, bn, 1, S) for sh in ("ll_o", "ll_down") for bn, S in ((144, 1), (176, 1), (176, 2), (176, 3))],
     "m1": [("vit_fc1", 1, 256, 1, 1), ("ll_gu", 1, 256, 1, 1), ("big_gu", 1, 256, 1, 1), ("big_down", 1, 256, 1, 1)],
 }
 
