@@ -9,15 +9,17 @@
 //   * a producer thread walks the range and keeps a ring of 3 chunks (K and V of 128 keys = 64 KiB by four 128-byte-swizzled
 //     TMA boxes; the last chunk of a row only its visible keys, in boxes of 32) in flight, across (row, head) boundaries and
 //     ahead of the programmatic-dependent-launch wait (every cached row was written at least one decode step ago);
-//   * four consumer warps run an online softmax over the chunks of a (row, head) segment: one key per thread for q.k, running
-//     maximum M with exp(M_old - M_new) rescaling of the per-warp P.V accumulators and per-thread partial sums - two 128-thread
-//     barriers per chunk, all reductions in a fixed order;
+//   * four consumer warps run an online softmax over the chunks of a (row, head) segment: q.k on the tensor cores (mma.sync
+//     m16n8k16 straight from the swizzled K tile by ldmatrix, q as a one-column B operand: 16 MMAs per warp and chunk instead of
+//     128 FFMAs + 128 conversions per thread - with the scalar loop the consumers, not HBM, set the pace), running maximum M with
+//     exp(M_old - M_new) rescaling of the per-warp P.V accumulators and per-lane partial sums - two 128-thread barriers per chunk,
+//     all reductions in a fixed order;
 //   * a segment that holds all chunks of its (row, head) writes the output row; otherwise it leaves (M, L, O[128]) in the
 //     workspace and the LAST segment of that (row, head) to arrive (one atomic per segment) combines them in segment order -
 //     deterministic: CUDA-graph replay == eager launches.
 // The new token's q / k / v (LoRA-B + RoPE, peft + modeling_llama.py:109-123) are computed at every segment start (a few
 // loads); the segment whose range holds the token's cache slot appends k / v (the torch.cat of modeling_llama.py:190-195) and
-// reads that row from shared memory instead of the tile. Arithmetic: fp32 softmax (modeling_llama.py:214), fp32 accumulation.
+// patches that row into the staged tile (the producer may have fetched the chunk before the append). Arithmetic: fp32 softmax (modeling_llama.py:214), fp32 accumulation.
 #include "decode_attn.cuh"
 
 namespace myr {
@@ -216,7 +218,19 @@ __global__ void __launch_bounds__(DS_THREADS) decode_attn_stream_kernel(const __
       }
       ds_sync();
     }
-    // q in registers as the score loop wants it: 4 interleaved partial dot products over the 16 16-byte units of a K row
+    // q as the B operand of the score MMAs (mma.sync.m16n8k16: A = 16 keys x 16 dims of the K tile, B = 16 dims x 8 columns of which
+    // only column 0 - lanes 0 .. 3 - carries q; sm.q holds fp16-representable values, so the cast is exact)
+    uint32_t qb[DA_DH / 16][2];
+#pragma unroll
+    for (int ks = 0; ks < DA_DH / 16; ++ks) {
+      qb[ks][0] = qb[ks][1] = 0u;
+      if (lane < 4) {
+        const __half2 lo = __floats2half2_rn(sm.q[ks * 16 + 2 * lane], sm.q[ks * 16 + 2 * lane + 1]);
+        const __half2 hi = __floats2half2_rn(sm.q[ks * 16 + 8 + 2 * lane], sm.q[ks * 16 + 8 + 2 * lane + 1]);
+        qb[ks][0] = *reinterpret_cast<const uint32_t*>(&lo);
+        qb[ks][1] = *reinterpret_cast<const uint32_t*>(&hi);
+      }
+    }
     float M = -INFINITY, l_t = 0.f;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const int v_half = lane >> 4, v_unit = (lane & 15) >> 1, v_sub = (lane & 1) * 8;
@@ -228,32 +242,59 @@ __global__ void __launch_bounds__(DS_THREADS) decode_attn_stream_kernel(const __
       mbar_wait(&full[st], phase);
       const uint8_t* sK = ring + st * DS_STAGE;
       const uint8_t* sV = sK + 2 * DS_TILE;
-      // ---- scores: one key per thread
-      float s = -INFINITY;
-      if (tid < n) {
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-        for (int i = 0; i < DA_DH / 8; ++i) {
-          const uint4 raw = (tid == off) ? reinterpret_cast<const uint4*>(sm.k)[i]
-                                         : *reinterpret_cast<const uint4*>(sK + (i >> 3) * DS_TILE + tid * 128 + (((i & 7) ^ (tid & 7)) << 4));
-          float kf[8];
-          da_unpack8(raw, kf);
-          const float4 qa = *reinterpret_cast<const float4*>(sm.q + i * 8), qb = *reinterpret_cast<const float4*>(sm.q + i * 8 + 4);
-          d0 = fmaf(kf[0], qa.x, d0); d1 = fmaf(kf[1], qa.y, d1); d2 = fmaf(kf[2], qa.z, d2); d3 = fmaf(kf[3], qa.w, d3);
-          d0 = fmaf(kf[4], qb.x, d0); d1 = fmaf(kf[5], qb.y, d1); d2 = fmaf(kf[6], qb.z, d2); d3 = fmaf(kf[7], qb.w, d3);
+      // the new token's K / V row is not in the tile (it was appended after the producer ran ahead): patch it in
+      if (off >= 0 && off < n) {
+        if (tid < 32) {
+          const int u = tid & 15;
+          const uint4 val = tid < 16 ? reinterpret_cast<const uint4*>(sm.k)[u] : reinterpret_cast<const uint4*>(sm.v)[u];
+          uint8_t* dst = const_cast<uint8_t*>(tid < 16 ? sK : sV) + (u >> 3) * DS_TILE + off * 128 + (((u & 7) ^ (off & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = val;
         }
-        s = ((d0 + d1) + (d2 + d3)) * p.scale;
+        ds_sync();
       }
-      float m = s;
+      // ---- scores on the tensor cores: warp w takes keys [32 w, 32 w + 32) as two 16-key tiles; the results land in the lanes
+      // with lane % 4 == 0 (fragment column 0): keys 32 w + 16 t + lane / 4 (+ 8). Before: one key per thread, 128 FFMAs and 128
+      // half -> float conversions each - the four consumer warps, not HBM, set the pace (1.85 us per 64 KB chunk).
+      float sc4[4];
+      {
+        const uint32_t sK_a = smem_u32(sK);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+          const int row = warp * 32 + t * 16 + (lane & 15);
+#pragma unroll
+          for (int ks = 0; ks < DA_DH / 16; ++ks) {
+            const int unit = (ks & 3) * 2 + (lane >> 4);  // 16-byte unit inside the 64-dim tile; rows are 128-byte-swizzled
+            uint32_t a[4];
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+                         : "r"(sK_a + (ks >> 2) * DS_TILE + row * 128 + ((unit ^ (row & 7)) << 4)));
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(qb[ks][0]), "r"(qb[ks][1]));
+          }
+          const int k0 = warp * 32 + t * 16 + (lane >> 2);
+          sc4[2 * t] = ((lane & 3) == 0 && k0 < n) ? c[0] * p.scale : -INFINITY;
+          sc4[2 * t + 1] = ((lane & 3) == 0 && k0 + 8 < n) ? c[2] * p.scale : -INFINITY;
+        }
+      }
+      float m = fmaxf(fmaxf(sc4[0], sc4[1]), fmaxf(sc4[2], sc4[3]));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       if (lane == 0) s_red[par][warp] = m;
       ds_sync();
       const float Mn = fmaxf(M, fmaxf(fmaxf(s_red[par][0], s_red[par][1]), fmaxf(s_red[par][2], s_red[par][3])));
       const float sc = __expf(M - Mn);  // 0 on the first chunk (M = -inf)
-      const float pj_own = (tid < n) ? __expf(s - Mn) : 0.f;
-      s_p[par][tid] = pj_own;
-      l_t = fmaf(l_t, sc, pj_own);
+      float p_sum = 0.f;
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float pj = sc4[i] > -INFINITY ? __expf(sc4[i] - Mn) : 0.f;
+          s_p[par][warp * 32 + (i >> 1) * 16 + (lane >> 2) + (i & 1) * 8] = pj;
+          p_sum += pj;
+        }
+      }
+      l_t = fmaf(l_t, sc, p_sum);
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] *= sc;
       M = Mn;
@@ -262,8 +303,7 @@ __global__ void __launch_bounds__(DS_THREADS) decode_attn_stream_kernel(const __
 #pragma unroll 4
       for (int j = warp; j < n; j += 4) {
         const float pj = s_p[par][j];
-        const uint2 raw = (j == off) ? *reinterpret_cast<const uint2*>(sm.v + lane * 4)
-                                     : *reinterpret_cast<const uint2*>(sV + v_half * DS_TILE + j * 128 + ((v_unit ^ (j & 7)) << 4) + v_sub);
+        const uint2 raw = *reinterpret_cast<const uint2*>(sV + v_half * DS_TILE + j * 128 + ((v_unit ^ (j & 7)) << 4) + v_sub);
         const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
         const float2 a = __half22float2(h2[0]), bb = __half22float2(h2[1]);
         acc[0] = fmaf(pj, a.x, acc[0]);
