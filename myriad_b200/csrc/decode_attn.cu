@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const DecodeAtt
 // with both; a shallower o_proj ring that would fit next to it costs more than it gains).
 struct DecodeAttnTmaParams {
   DecodeAttnParams a;
-  int kv_cap;  // rows per box (multiple of 8, <= 256)
+  int kv_cap;      // rows per box (multiple of 8, <= 256)
+  int mma_scores;  // 1: q.k on mma.sync (default); 0: the scalar loop whose summation order the persistent decode kernel shares (MYR_DA_MMA=0)
 };
 
 __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __grid_constant__ CUtensorMap tmK,
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
 
   // ---- phase 0: q / k / v of the new token: LoRA, rotation, cache append (one rotary pair per thread)
   const __half* row = p.qkv + (size_t)b * p.ldq;
+  __half ko1 = __float2half_rn(0.f), ko2 = ko1, vo1 = ko1, vo2 = ko1;  // this thread's rotary pair of the new token's k / v
   if (tid < DA_DH / 2) {
     const int j = tid, half = DA_DH / 2;
     float q1 = __half2float(__ldcg(row + h * DA_DH + j)), q2 = __half2float(__ldcg(row + h * DA_DH + half + j));
@@ -295,10 +297,8 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
     // fp16 rounding of the rotated q / k and of v: the values the prefill path stores (q in place, k / v in the cache)
     sm.q[j] = round_f16(q1 * c - q2 * sn);
     sm.q[half + j] = round_f16(q2 * c + q1 * sn);
-    const __half ko1 = __float2half_rn(k1 * c - k2 * sn), ko2 = __float2half_rn(k2 * c + k1 * sn);
-    const __half vo1 = __float2half_rn(v1), vo2 = __float2half_rn(v2);
-    sm.k[j] = ko1; sm.k[half + j] = ko2;
-    sm.v[j] = vo1; sm.v[half + j] = vo2;
+    ko1 = __float2half_rn(k1 * c - k2 * sn); ko2 = __float2half_rn(k2 * c + k1 * sn);
+    vo1 = __float2half_rn(v1); vo2 = __float2half_rn(v2);
     if (off >= 0 && off < p.Smax) {
       __half* kd = kbase + (size_t)off * p.c_ts;
       __half* vd = vbase + (size_t)off * p.c_ts;
@@ -307,19 +307,64 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
     }
   }
   mbar_wait(&bar, 0);  // K / V tiles have landed (requested before the wait)
+  // the new token's row is not in the tiles (they were requested before its append): every thread of phase 0 puts its own four
+  // values in (element e of a row sits in tile e / 64, 16-byte unit ((e / 8) & 7) ^ (row & 7))
+  if (tid < DA_DH / 2 && off >= 0 && off < kvl) {
+    auto slot = [&](uint8_t* tile0, int e) {
+      return reinterpret_cast<__half*>(tile0 + (e >> 6) * tile_bytes + off * 128 + ((((e >> 3) & 7) ^ (off & 7)) << 4) + (e & 7) * 2);
+    };
+    *slot(sK, tid) = ko1; *slot(sK, DA_DH / 2 + tid) = ko2;
+    *slot(sV, tid) = vo1; *slot(sV, DA_DH / 2 + tid) = vo2;
+  }
   __syncthreads();
   stamp(2);
 
-  // ---- phase 1: scores, one key per thread and pass; rows come from the swizzled tiles (the new token's from sm.k)
-  for (int j = tid; j < kvl; j += DA_THREADS) {
-    float d[4] = {0.f, 0.f, 0.f, 0.f};
+  // ---- phase 1: scores on the tensor cores (mma.sync.m16n8k16: A = 16 keys x 16 dims of the swizzled K tile by ldmatrix, B = q in
+  // column 0): 16-key tiles dealt round-robin to the warps, results in the lanes with lane % 4 == 0. One key per thread and pass with
+  // 128 FFMAs + 128 conversions each took ~0.6 us of the launch's latency chain.
+  if (!pp.mma_scores) {
+    for (int j = tid; j < kvl; j += DA_THREADS) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < DA_DH / 8; ++i) {
-      const uint4 raw = (j == off) ? reinterpret_cast<const uint4*>(sm.k)[i]
-                                   : *reinterpret_cast<const uint4*>(sK + (i >> 3) * tile_bytes + j * 128 + (((i & 7) ^ (j & 7)) << 4));
-      da_dot8(raw, sm.q + i * 8, d);
+      for (int i = 0; i < DA_DH / 8; ++i)
+        da_dot8(*reinterpret_cast<const uint4*>(sK + (i >> 3) * tile_bytes + j * 128 + (((i & 7) ^ (j & 7)) << 4)), sm.q + i * 8, d);
+      s_scores[j] = da_dot_finish(d) * p.scale;
     }
-    s_scores[j] = da_dot_finish(d) * p.scale;
+  } else {
+    uint32_t qb[DA_DH / 16][2];
+#pragma unroll
+    for (int ks = 0; ks < DA_DH / 16; ++ks) {
+      qb[ks][0] = qb[ks][1] = 0u;
+      if (lane < 4) {  // sm.q holds fp16-representable values: the cast is exact
+        const __half2 lo = __floats2half2_rn(sm.q[ks * 16 + 2 * lane], sm.q[ks * 16 + 2 * lane + 1]);
+        const __half2 hi = __floats2half2_rn(sm.q[ks * 16 + 8 + 2 * lane], sm.q[ks * 16 + 8 + 2 * lane + 1]);
+        qb[ks][0] = *reinterpret_cast<const uint32_t*>(&lo);
+        qb[ks][1] = *reinterpret_cast<const uint32_t*>(&hi);
+      }
+    }
+    const uint32_t sK_a = smem_u32(sK);
+    const int n_mt = (kvl + 15) >> 4;
+    for (int mt = warp; mt < n_mt; mt += 4) {
+      float c4[4] = {0.f, 0.f, 0.f, 0.f};
+      int row = mt * 16 + (lane & 15);
+      if (row >= pp.kv_cap) row = pp.kv_cap - 1;  // kv_cap is a multiple of 8, not of 16: stay inside the tile (those keys are masked)
+#pragma unroll
+      for (int ks = 0; ks < DA_DH / 16; ++ks) {
+        const int unit = (ks & 3) * 2 + (lane >> 4);
+        uint32_t a4[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a4[0]), "=r"(a4[1]), "=r"(a4[2]), "=r"(a4[3])
+                     : "r"(sK_a + (ks >> 2) * tile_bytes + row * 128 + ((unit ^ (row & 7)) << 4)));
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(c4[0]), "+f"(c4[1]), "+f"(c4[2]), "+f"(c4[3])
+                     : "r"(a4[0]), "r"(a4[1]), "r"(a4[2]), "r"(a4[3]), "r"(qb[ks][0]), "r"(qb[ks][1]));
+      }
+      if ((lane & 3) == 0) {
+        const int k0 = mt * 16 + (lane >> 2);
+        if (k0 < kvl) s_scores[k0] = c4[0] * p.scale;
+        if (k0 + 8 < kvl) s_scores[k0 + 8] = c4[2] * p.scale;
+      }
+    }
   }
   __syncthreads();
   stamp(3);
@@ -359,8 +404,7 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
       const int j = j0 + 4 * u;
       const int jc = j < kvl ? j : warp;  // clamped (the slot is in the tile): loaded, never used
       pj[u] = s_scores[jc];
-      raw[u] = (jc == off) ? *reinterpret_cast<const uint2*>(sm.v + lane * 4)
-                           : *reinterpret_cast<const uint2*>(sV + v_half * tile_bytes + jc * 128 + ((v_unit ^ (jc & 7)) << 4) + v_sub);
+      raw[u] = *reinterpret_cast<const uint2*>(sV + v_half * tile_bytes + jc * 128 + ((v_unit ^ (jc & 7)) << 4) + v_sub);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -450,6 +494,10 @@ extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_
         const int rc = make_tmap_f16(maps[i], ptrs[i], 4, dims, strides, box);
         if (rc) return rc;
       }
+    }
+    {
+      const char* e = getenv("MYR_DA_MMA");  // read per launch: the parity test of the persistent decode kernel switches it
+      pp.mma_scores = (e && e[0] == '0') ? 0 : 1;
     }
     const size_t smem = (size_t)pp.kv_cap * (4 * 128 + 4) + 1024;
     static bool attr2 = false;
