@@ -221,7 +221,10 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
   const int tile_bytes = pp.kv_cap * 128;  // one [kv_cap][64 halfs] box
   uint8_t* sK = tiles;                     // [2 dh halves][kv_cap][128 B], 16-byte unit u of row r at unit u ^ (r & 7)
   uint8_t* sV = tiles + 2 * tile_bytes;
-  float* s_scores = reinterpret_cast<float*>(tiles + 4 * tile_bytes);  // [kv_cap]
+  uint8_t* zpad = tiles + 4 * tile_bytes;                               // 2 KB of zeros: ldmatrix rows past the end of the second V tile
+  float* s_scores = reinterpret_cast<float*>(zpad + 2048);              // [kv_cap]
+  __half* s_ph = reinterpret_cast<__half*>(s_scores + ((pp.kv_cap + 3) & ~3));  // [272] P as fp16 head ...
+  __half* s_pl = s_ph + 272;                                            // [272] ... and fp16 remainder (tensor-core path)
   __shared__ DecodeAttnSmem sm;
   __shared__ uint64_t bar;
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
     mbar_init(&bar, 1);
     fence_mbar_init();
   }
+  reinterpret_cast<uint4*>(zpad)[tid] = make_uint4(0u, 0u, 0u, 0u);  // 128 threads x 16 bytes
   __syncthreads();
   pdl_launch_dependents();
   long long* tr = (p.trace && tid == 0) ? p.trace + (blockIdx.y * gridDim.x + blockIdx.x) * 6 : nullptr;
@@ -316,21 +320,25 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
     *slot(sK, tid) = ko1; *slot(sK, DA_DH / 2 + tid) = ko2;
     *slot(sV, tid) = vo1; *slot(sV, DA_DH / 2 + tid) = vo2;
   }
+  if (pp.mma_scores) {
+    // P V runs over whole 16-key steps: the V rows between the visible keys and the end of the last step meet P = 0, but cache slots
+    // nobody wrote yet may hold NaN patterns - zero them in the staged tiles
+    const int r_end = min((kvl + 15) & ~15, pp.kv_cap);
+    for (int i = tid; i < (r_end - kvl) * 16; i += DA_THREADS) {
+      const int r = kvl + (i >> 4), u = i & 15;
+      *reinterpret_cast<uint4*>(sV + (u >> 3) * tile_bytes + r * 128 + ((u & 7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
   __syncthreads();
   stamp(2);
 
-  // ---- phase 1: scores on the tensor cores (mma.sync.m16n8k16: A = 16 keys x 16 dims of the swizzled K tile by ldmatrix, B = q in
-  // column 0): 16-key tiles dealt round-robin to the warps, results in the lanes with lane % 4 == 0. One key per thread and pass with
-  // 128 FFMAs + 128 conversions each took ~0.6 us of the launch's latency chain.
-  if (!pp.mma_scores) {
-    for (int j = tid; j < kvl; j += DA_THREADS) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < DA_DH / 8; ++i)
-        da_dot8(*reinterpret_cast<const uint4*>(sK + (i >> 3) * tile_bytes + j * 128 + (((i & 7) ^ (j & 7)) << 4)), sm.q + i * 8, d);
-      s_scores[j] = da_dot_finish(d) * p.scale;
-    }
-  } else {
+  if (pp.mma_scores) {
+    // ---- tensor-core path (default). The launch is a latency chain with HBM idle, so every phase is cut to a few hundred cycles:
+    // scores by mma.sync.m16n8k16 (A = 16 keys x 16 dims of the swizzled K tile by ldmatrix, B = q in column 0; a warp's up to four
+    // key tiles run as independent accumulator chains), softmax statistics straight from the score registers (two barriers), and
+    // O = P V by mma.sync too: A = P in row 0, split into an fp16 head and an fp16 remainder (two MMAs: fp32-grade products), B = V
+    // through ldmatrix.trans; a warp owns 32 output dims over all keys, so no cross-warp reduction follows.
+    // (Scalar version: one key per thread and pass with 128 FFMAs + 128 conversions, then 41 keys per warp of P V: 1.3 + 1.5 us.)
     uint32_t qb[DA_DH / 16][2];
 #pragma unroll
     for (int ks = 0; ks < DA_DH / 16; ++ks) {
@@ -342,29 +350,159 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_tma_kernel(const __gri
         qb[ks][1] = *reinterpret_cast<const uint32_t*>(&hi);
       }
     }
-    const uint32_t sK_a = smem_u32(sK);
-    const int n_mt = (kvl + 15) >> 4;
-    for (int mt = warp; mt < n_mt; mt += 4) {
-      float c4[4] = {0.f, 0.f, 0.f, 0.f};
-      int row = mt * 16 + (lane & 15);
+    const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+    const int n_mt = (kvl + 15) >> 4;  // <= 16: tiles warp, warp + 4, warp + 8, warp + 12
+    // one warp per scheduler: every instruction's latency shows, so all address arithmetic is hoisted out of the MMA loops
+    float c[4][4], c2[4][4];  // even / odd k-steps: short dependent chains
+    uint32_t kaddr[4][4];     // [tile][k-step mod 4]: row * 128 + swizzled 16-byte unit
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      c[t][0] = c[t][1] = c[t][2] = c[t][3] = 0.f;
+      c2[t][0] = c2[t][1] = c2[t][2] = c2[t][3] = 0.f;
+      int row = (warp + 4 * t) * 16 + (lane & 15);
       if (row >= pp.kv_cap) row = pp.kv_cap - 1;  // kv_cap is a multiple of 8, not of 16: stay inside the tile (those keys are masked)
 #pragma unroll
-      for (int ks = 0; ks < DA_DH / 16; ++ks) {
-        const int unit = (ks & 3) * 2 + (lane >> 4);
-        uint32_t a4[4];
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(a4[0]), "=r"(a4[1]), "=r"(a4[2]), "=r"(a4[3])
-                     : "r"(sK_a + (ks >> 2) * tile_bytes + row * 128 + ((unit ^ (row & 7)) << 4)));
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                     : "+f"(c4[0]), "+f"(c4[1]), "+f"(c4[2]), "+f"(c4[3])
-                     : "r"(a4[0]), "r"(a4[1]), "r"(a4[2]), "r"(a4[3]), "r"(qb[ks][0]), "r"(qb[ks][1]));
-      }
-      if ((lane & 3) == 0) {
-        const int k0 = mt * 16 + (lane >> 2);
-        if (k0 < kvl) s_scores[k0] = c4[0] * p.scale;
-        if (k0 + 8 < kvl) s_scores[k0 + 8] = c4[2] * p.scale;
+      for (int u4 = 0; u4 < 4; ++u4) kaddr[t][u4] = sK_a + row * 128 + (((u4 * 2 + (lane >> 4)) ^ (row & 7)) << 4);
+    }
+#pragma unroll
+    for (int ks = 0; ks < DA_DH / 16; ++ks) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (warp + 4 * t < n_mt) {
+          uint32_t a4[4];
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(a4[0]), "=r"(a4[1]), "=r"(a4[2]), "=r"(a4[3])
+                       : "r"(kaddr[t][ks & 3] + (ks >> 2) * tile_bytes));
+          float (&cc)[4] = (ks & 1) ? c2[t] : c[t];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(cc[0]), "+f"(cc[1]), "+f"(cc[2]), "+f"(cc[3])
+                       : "r"(a4[0]), "r"(a4[1]), "r"(a4[2]), "r"(a4[3]), "r"(qb[ks][0]), "r"(qb[ks][1]));
+        }
       }
     }
+    stamp(3);
+    // scores of keys (warp + 4 t) * 16 + lane / 4 (+ 8) sit in the lanes with lane % 4 == 0
+    float sv[4][2];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k0 = (warp + 4 * t) * 16 + (lane >> 2);
+      sv[t][0] = ((lane & 3) == 0 && k0 < kvl) ? (c[t][0] + c2[t][0]) * p.scale : -INFINITY;
+      sv[t][1] = ((lane & 3) == 0 && k0 + 8 < kvl) ? (c[t][2] + c2[t][2]) * p.scale : -INFINITY;
+      mx = fmaxf(mx, fmaxf(sv[t][0], sv[t][1]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sm.red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(sm.red[0], sm.red[1]), fmaxf(sm.red[2], sm.red[3]));
+    // P = exp(s - max) goes to shared memory as an fp16 head and an fp16 remainder (head + remainder carries 22 bits of P): the two
+    // A operands of the P V MMAs; the row sum is taken over the fp32 values
+    float l = 0.f;
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (warp + 4 * t < n_mt) {
+          const int k0 = (warp + 4 * t) * 16 + (lane >> 2);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float ex = sv[t][e] > -INFINITY ? __expf(sv[t][e] - mx) : 0.f;
+            const __half hd = __float2half_rn(ex);
+            s_ph[k0 + 8 * e] = hd;
+            s_pl[k0 + 8 * e] = __float2half_rn(ex - __half2float(hd));
+            l += ex;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) sm.acc[0][warp] = l;
+    __syncthreads();
+    l = (sm.acc[0][0] + sm.acc[0][1]) + (sm.acc[0][2] + sm.acc[0][3]);
+    stamp(4);
+    // ---- O = P V: this warp's dims [32 warp, 32 warp + 32) over all keys; A = P in row 0 of the fragment (lanes 0 .. 3)
+    float o4[4][4][2];  // [dim tile][head / remainder x even / odd key step][row-0 columns]: 16 independent chains
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) o4[nt][v][0] = o4[nt][v][1] = 0.f;
+    const int dw = warp * 32;
+    uint32_t vaddr[2];
+    {
+      const int r_l = (lane & 7) + ((lane >> 3) & 1) * 8;  // key row inside a 16-key step; (k0 + r_l) & 7 == lane & 7
+#pragma unroll
+      for (int n2 = 0; n2 < 2; ++n2) {
+        const int d0 = dw + n2 * 16;
+        vaddr[n2] = sV_a + (d0 >> 6) * tile_bytes + r_l * 128 + (((((d0 & 63) >> 3) + (lane >> 4)) ^ (lane & 7)) << 4);
+      }
+    }
+    const uint32_t ph_a = smem_u32(s_ph) + lane * 4, pl_a = smem_u32(s_pl) + lane * 4;
+    auto pv_step = [&](int ks, int par) {
+      uint32_t ah0 = 0u, ah2 = 0u, al0 = 0u, al2 = 0u;
+      if (lane < 4) {
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ah0) : "r"(ph_a + ks * 32));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ah2) : "r"(ph_a + ks * 32 + 16));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(al0) : "r"(pl_a + ks * 32));
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(al2) : "r"(pl_a + ks * 32 + 16));
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < 2; ++n2) {
+        uint32_t bv[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(bv[0]), "=r"(bv[1]), "=r"(bv[2]), "=r"(bv[3])
+                     : "r"(vaddr[n2] + ks * 2048));
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+          float dmy0 = 0.f, dmy1 = 0.f, dmy2 = 0.f, dmy3 = 0.f;  // rows 8 .. 15 of the fragment: always zero (A has only row 0)
+          float (&oh)[2] = o4[2 * n2 + q2][par];
+          float (&ol)[2] = o4[2 * n2 + q2][2 + par];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(oh[0]), "+f"(oh[1]), "+f"(dmy0), "+f"(dmy1)
+                       : "r"(ah0), "r"(0u), "r"(ah2), "r"(0u), "r"(bv[2 * q2]), "r"(bv[2 * q2 + 1]));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(ol[0]), "+f"(ol[1]), "+f"(dmy2), "+f"(dmy3)
+                       : "r"(al0), "r"(0u), "r"(al2), "r"(0u), "r"(bv[2 * q2]), "r"(bv[2 * q2 + 1]));
+        }
+      }
+    };
+    for (int ks = 0; ks + 1 < n_mt; ks += 2) {
+      pv_step(ks, 0);
+      pv_step(ks + 1, 1);
+    }
+    if (n_mt & 1) pv_step(n_mt - 1, 0);
+    if (lane < 4) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      __half* op = p.out + (size_t)b * p.ldo + h * DA_DH + dw + 2 * lane;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float x0 = (o4[nt][0][0] + o4[nt][1][0]) + (o4[nt][2][0] + o4[nt][3][0]);  // heads (even + odd steps) + remainders
+        const float x1 = (o4[nt][0][1] + o4[nt][1][1]) + (o4[nt][2][1] + o4[nt][3][1]);
+        *reinterpret_cast<__half2*>(op + nt * 8) = __floats2half2_rn(x0 * inv, x1 * inv);
+      }
+    }
+    if (p.next_layer_stride) {
+      // ask L2 for the next layer's slice of the cache (its attention runs ~80 us from now; weights are loaded evict-first, so the
+      // lines survive until then) - after the output is on its way: nothing waits for these
+      const __half* kn = kbase + p.next_layer_stride;
+      const __half* vn = vbase + p.next_layer_stride;
+      for (int j = tid; j < 2 * kvl; j += DA_THREADS) {  // one 128-byte line = half a K or V row
+        const size_t o = (size_t)(j >> 1) * p.c_ts + (j & 1) * 64;
+        prefetch_l2(kn + o);
+        prefetch_l2(vn + o);
+      }
+    }
+    stamp(5);
+    return;
+  }
+
+  // ---- scalar path (MYR_DA_MMA=0): the summation order the persistent decode kernel (decode_mega.cu) shares bit for bit
+  for (int j = tid; j < kvl; j += DA_THREADS) {
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < DA_DH / 8; ++i)
+      da_dot8(*reinterpret_cast<const uint4*>(sK + (i >> 3) * tile_bytes + j * 128 + (((i & 7) ^ (j & 7)) << 4)), sm.q + i * 8, d);
+    s_scores[j] = da_dot_finish(d) * p.scale;
   }
   __syncthreads();
   stamp(3);
@@ -499,7 +637,7 @@ extern "C" int myr_decode_attention(const myr_decode_attn_args* a, void* stream_
       const char* e = getenv("MYR_DA_MMA");  // read per launch: the parity test of the persistent decode kernel switches it
       pp.mma_scores = (e && e[0] == '0') ? 0 : 1;
     }
-    const size_t smem = (size_t)pp.kv_cap * (4 * 128 + 4) + 1024;
+    const size_t smem = (size_t)pp.kv_cap * (4 * 128 + 4) + 1024 + 2048 + 16 + 2 * 272 * 2;
     static bool attr2 = false;
     if (!attr2) {
       MYR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
