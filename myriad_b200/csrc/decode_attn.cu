@@ -1,12 +1,14 @@
-// Decode-step attention for one new token per sequence (HBM/latency-bound, CUDA cores): one CTA per (head, batch row) fuses
+// Decode-step attention for one new token per sequence (HBM / latency-bound): one CTA per (head, batch row) fuses
 //   LoRA-B update of q and v  (peft, myriad.py:171-178)         q += s * B_q (A_q x),  v += s * B_v (A_v x)
 //   RoPE of q and k           (modeling_llama.py:109-123)
 //   KV-cache append           (replaces the torch.cat growth of modeling_llama.py:190-195)
 //   softmax(q K^T / sqrt(dh)) V over the cache (modeling_llama.py:197-215; fp32 softmax)
 // which the prefill path runs as myr_rope_cache + the tcgen05 flash kernel. With a single query row the 128-row MMA tile
-// of the flash kernel is 99 % padding and its TMA -> MMA -> softmax -> MMA chain is pure latency; here every thread streams
-// 16-byte pieces of K and V rows straight from the cache. Deterministic (fixed reduction order): CUDA-graph replays of the
-// decode step reproduce eager launches bit for bit.
+// of the flash kernel is 99 % padding and its TMA -> MMA -> softmax -> MMA chain is pure latency. Two variants: the register
+// variant (every thread streams 16-byte pieces of K and V rows straight from the cache, CUDA cores) and, for caches of up to 256
+// slots with a known bound (the captured decode step), the TMA variant: K / V of the (head, row) land in swizzled shared-memory
+// tiles ahead of the dependency wait and q.K / P.V run on mma.sync from those tiles. Deterministic (fixed reduction order):
+// CUDA-graph replays of the decode step reproduce eager launches bit for bit.
 #include "decode_attn.cuh"
 
 namespace myr {

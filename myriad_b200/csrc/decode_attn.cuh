@@ -43,8 +43,9 @@ __device__ __forceinline__ float da_lora_dot(const __half* __restrict__ b, int r
   return a;
 }
 
-// q . k over one 16-byte unit of the K row (8 halfs): four interleaved partial sums d[e % 4] - the same order in every decode-attention
-// kernel (they must agree bit for bit: tests compare the persistent kernel, the register and the shared-memory variants). A single
+// q . k over one 16-byte unit of the K row (8 halfs): four interleaved partial sums d[e % 4] - the same order in every SCALAR score
+// loop (the register variant, the persistent decode kernel of decode_mega.cu and the MYR_DA_MMA=0 path of the TMA variant agree bit
+// for bit; the default TMA / long-cache kernels compute the scores on mma.sync, another - equally deterministic - order). A single
 // accumulator is a 128-deep dependent FMA chain (~0.3 us per key at 4 clk per FMA); four chains of 32 and 16-byte q reads cut the
 // score phase of a 163-slot cache from ~1.3 us to about half.
 __device__ __forceinline__ void da_dot8(const uint4& kraw, const float* __restrict__ q8, float (&d)[4]) {
