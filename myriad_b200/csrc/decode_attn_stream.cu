@@ -152,7 +152,35 @@ __global__ void __launch_bounds__(DS_THREADS) decode_attn_stream_kernel(const __
   int st = 0;
   uint32_t phase = 0;
   int idx = lo;
-  bool waited = false;
+  // inputs of a segment's prologue (threads 0 .. 63: one rotary pair each), requested one segment ahead
+  struct {
+    float cs, sn;
+    uint4 lb[4], xq, xv;
+    __half q1, q2, k1, k2, v1, v2;
+  } pro = {};
+  auto pro_load = [&](int b, int h) {
+    if (tid >= DA_DH / 2) return;
+    const int pos = s_pos[b], j = tid, half = DA_DH / 2;
+    pro.cs = p.cos_t[(size_t)pos * half + j];
+    pro.sn = p.sin_t[(size_t)pos * half + j];
+    const __half* row = p.qkv + (size_t)b * p.ldq;
+    if (p.lora_r) {
+      pro.lb[0] = __ldg(reinterpret_cast<const uint4*>(p.lora_bq + (size_t)(h * DA_DH + j) * 8));
+      pro.lb[1] = __ldg(reinterpret_cast<const uint4*>(p.lora_bq + (size_t)(h * DA_DH + half + j) * 8));
+      pro.lb[2] = __ldg(reinterpret_cast<const uint4*>(p.lora_bv + (size_t)(h * DA_DH + j) * 8));
+      pro.lb[3] = __ldg(reinterpret_cast<const uint4*>(p.lora_bv + (size_t)(h * DA_DH + half + j) * 8));
+      pro.xq = __ldcg(reinterpret_cast<const uint4*>(row + 3 * HD));
+      pro.xv = __ldcg(reinterpret_cast<const uint4*>(row + 3 * HD + 8));
+    }
+    pro.q1 = __ldcg(row + h * DA_DH + j);
+    pro.q2 = __ldcg(row + h * DA_DH + half + j);
+    pro.k1 = __ldcg(row + HD + h * DA_DH + j);
+    pro.k2 = __ldcg(row + HD + h * DA_DH + half + j);
+    pro.v1 = __ldcg(row + 2 * HD + h * DA_DH + j);
+    pro.v2 = __ldcg(row + 2 * HD + h * DA_DH + half + j);
+  };
+  pdl_wait();  // qkv of this step
+  pro_load(q.b, q.h);
   while (idx < hi) {
     // ---- segment: chunks [c0, c1) of (row b, head h)
     const int b = q.b, h = q.h, c0 = q.c;
@@ -163,32 +191,19 @@ __global__ void __launch_bounds__(DS_THREADS) decode_attn_stream_kernel(const __
     __half* vbase = p.vcache + (size_t)b * p.c_bs + h * DA_DH;
     const bool owns_new = off_g >= c0 * DS_CH && off_g < c1 * DS_CH && off_g < p.Smax;
     {
-      // the new token's q / k / v: LoRA, rotation (one rotary pair per thread), cache append by the owning segment
-      const int pos = s_pos[b];  // (one round trip for the whole segment prologue: nothing below depends on another load)
-      const int jr = tid & (DA_DH / 2 - 1);
-      const float cs = p.cos_t[(size_t)pos * (DA_DH / 2) + jr], sn = p.sin_t[(size_t)pos * (DA_DH / 2) + jr];
-      uint4 lb[4] = {};
-      if (p.lora_r && tid < DA_DH / 2) {
-        lb[0] = __ldg(reinterpret_cast<const uint4*>(p.lora_bq + (size_t)(h * DA_DH + tid) * 8));
-        lb[1] = __ldg(reinterpret_cast<const uint4*>(p.lora_bq + (size_t)(h * DA_DH + DA_DH / 2 + tid) * 8));
-        lb[2] = __ldg(reinterpret_cast<const uint4*>(p.lora_bv + (size_t)(h * DA_DH + tid) * 8));
-        lb[3] = __ldg(reinterpret_cast<const uint4*>(p.lora_bv + (size_t)(h * DA_DH + DA_DH / 2 + tid) * 8));
-      }
-      if (!waited) {
-        pdl_wait();
-        waited = true;
-      }
+      // the new token's q / k / v: LoRA, rotation (one rotary pair per thread), cache append by the owning segment. Its inputs
+      // (`pro`) were requested one segment ago (below), so no memory round trip sits between two segments.
       ds_sync();  // the previous segment is done with sm.q / sm.k / sm.v / sm.acc
-      const __half* row = p.qkv + (size_t)b * p.ldq;
       if (tid < DA_DH / 2) {
         const int j = tid, half = DA_DH / 2;
-        float q1 = __half2float(__ldcg(row + h * DA_DH + j)), q2 = __half2float(__ldcg(row + h * DA_DH + half + j));
-        const float k1 = __half2float(__ldcg(row + HD + h * DA_DH + j)), k2 = __half2float(__ldcg(row + HD + h * DA_DH + half + j));
-        float v1 = __half2float(__ldcg(row + 2 * HD + h * DA_DH + j)), v2 = __half2float(__ldcg(row + 2 * HD + h * DA_DH + half + j));
+        const float cs = pro.cs, sn = pro.sn;
+        float q1 = __half2float(pro.q1), q2 = __half2float(pro.q2);
+        const float k1 = __half2float(pro.k1), k2 = __half2float(pro.k2);
+        float v1 = __half2float(pro.v1), v2 = __half2float(pro.v2);
         if (p.lora_r) {
           float xq[8], xv[8];
-          da_unpack8(__ldcg(reinterpret_cast<const uint4*>(row + 3 * HD)), xq);
-          da_unpack8(__ldcg(reinterpret_cast<const uint4*>(row + 3 * HD + 8)), xv);
+          da_unpack8(pro.xq, xq);
+          da_unpack8(pro.xv, xv);
           auto dot8 = [](const uint4& wrow, const float (&xa)[8]) {  // same order of operations as da_lora_dot
             float w[8];
             da_unpack8(wrow, w);
@@ -197,10 +212,10 @@ __global__ void __launch_bounds__(DS_THREADS) decode_attn_stream_kernel(const __
             for (int r = 0; r < 8; ++r) acc = fmaf(w[r], xa[r], acc);
             return acc;
           };
-          q1 = fmaf(p.lora_scale, dot8(lb[0], xq), q1);
-          q2 = fmaf(p.lora_scale, dot8(lb[1], xq), q2);
-          v1 = fmaf(p.lora_scale, dot8(lb[2], xv), v1);
-          v2 = fmaf(p.lora_scale, dot8(lb[3], xv), v2);
+          q1 = fmaf(p.lora_scale, dot8(pro.lb[0], xq), q1);
+          q2 = fmaf(p.lora_scale, dot8(pro.lb[1], xq), q2);
+          v1 = fmaf(p.lora_scale, dot8(pro.lb[2], xv), v1);
+          v2 = fmaf(p.lora_scale, dot8(pro.lb[3], xv), v2);
         }
         // fp16 rounding of the rotated q / k and of v: the values the prefill path stores (q in place, k / v in the cache)
         sm.q[j] = round_f16(q1 * cs - q2 * sn);
@@ -217,6 +232,11 @@ __global__ void __launch_bounds__(DS_THREADS) decode_attn_stream_kernel(const __
         }
       }
       ds_sync();
+      // request the NEXT segment's inputs now: they arrive under this segment's chunks
+      if (c1 == ncb && idx + (c1 - c0) < hi) {
+        const bool wrap = h + 1 == p.H;
+        pro_load(wrap ? b + 1 : b, wrap ? 0 : h + 1);
+      }
     }
     // q as the B operand of the score MMAs (mma.sync.m16n8k16: A = 16 keys x 16 dims of the K tile, B = 16 dims x 8 columns of which
     // only column 0 - lanes 0 .. 3 - carries q; sm.q holds fp16-representable values, so the cast is exact)
