@@ -56,7 +56,22 @@ def test_argument_validation_needs_no_gpu():
     b = K.AttnArgs()
     assert lib().myr_attention_fwd(ctypes.byref(b), None) == -1
     assert "attention" in last_error()
-
+    # the fused training kernels state their limits instead of falling back silently
+    import torch
+    L = lib()
+    assert L.myr_attn_bwd_small_supported(164, 164, 128) == 1 and L.myr_attn_bwd_small_supported(81, 81, 64) == 1
+    assert L.myr_attn_bwd_small_supported(33, 256, 64) == 1
+    assert L.myr_attn_bwd_small_supported(81, 257, 64) == 0 and L.myr_attn_bwd_small_supported(16, 16, 96) == 0
+    t = torch.zeros(4, 96, dtype=torch.float16)
+    ptr, i64 = ctypes.c_void_p(t.data_ptr()), ctypes.c_int64
+    triple = [ptr, i64(96), i64(384)]
+    rc = L.myr_attn_bwd_small(*(triple * 7), 1, 1, 4, 4, 96, ctypes.c_float(0.1), 0, None, None)
+    assert rc == -1 and "dh must be 64 or 128" in last_error()
+    x = torch.zeros(4, 100, dtype=torch.float16)
+    px = ctypes.c_void_p(x.data_ptr())
+    rc = L.myr_lora_fwd(px, i64(100), px, px, px, px, px, i64(100), i64(0), i64(0), 4, 100, 8, ctypes.c_float(1.0), ctypes.c_float(0.0),
+                        ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0), None)
+    assert rc == -1 and "lora_fwd" in last_error()
 
 def test_no_cpu_fallback_in_product():
     """The product path never imports the oracle (the oracle is the checker, not a fallback)."""
